@@ -1,0 +1,177 @@
+/*
+ * gd_raster.h -- C ABI of the B200-native differentiable Gaussian-splat rasteriser.
+ *
+ * Drop-in boundary for the reference's native module `diff_gaussian_rasterization._C`
+ * (reference: Garment_3DGS/gaussiansplatting/submodules/diff-gaussian-rasterization, "DGR/"):
+ *
+ *   gd_raster_forward   replaces  RasterizeGaussiansCUDA          DGR/rasterize_points.cu:35-119
+ *                                 -> CudaRasterizer::Rasterizer::forward
+ *                                                                 DGR/cuda_rasterizer/rasterizer_impl.cu:197-339
+ *   gd_raster_backward  replaces  RasterizeGaussiansBackwardCUDA  DGR/rasterize_points.cu:121-208
+ *                                 -> CudaRasterizer::Rasterizer::backward
+ *                                                                 DGR/cuda_rasterizer/rasterizer_impl.cu:343-447
+ *   gd_mark_visible     replaces  markVisible                     DGR/rasterize_points.cu:210-229
+ *   gd_raster_state_bytes / gd_raster_state_view replace the resize callbacks and the
+ *   GeometryState/BinningState/ImageState::fromChunk carving
+ *                                                                 DGR/cuda_rasterizer/rasterizer_impl.cu:155-193
+ *                                                                 DGR/rasterize_points.cu:27-33
+ *
+ * Differences from the reference boundary, all deliberate:
+ *   - plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless
+ *     the field name ends in _host;
+ *   - B >= 1 camera views are rasterised by ONE call (the reference is called once per view,
+ *     Garment_3DGS/threestudio/systems/GaussianDreamer.py:189-191); B = 1 reproduces it;
+ *   - the caller owns every buffer; the library never allocates and never synchronises with the
+ *     host: the instance count stays on the device (the reference does a blocking cudaMemcpy,
+ *     rasterizer_impl.cu:282). The caller sizes the instance arena (`max_rendered`) up front and
+ *     reads back `counters` when it wants the count / the overflow flag;
+ *   - an explicit cudaStream_t (the reference launches on the legacy default stream).
+ *
+ * Conventions (identical to the reference): viewmatrix/projmatrix are the TRANSPOSED 4x4
+ * matrices, read as matrix[c*4+r]; quaternions are (r,x,y,z) and are not normalised; tiles are
+ * 16x16; all floating point data is fp32; images are CHW.
+ */
+#ifndef GD_RASTER_H_
+#define GD_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_MAX_VIEWS 32
+#define GD_TILE 16
+
+/* Return codes. Negative = error; gd_last_error() holds a message for the calling thread. */
+#define GD_OK 0
+#define GD_ERR_INVALID_ARG (-1)
+#define GD_ERR_WORKSPACE_TOO_SMALL (-2)
+#define GD_ERR_CUDA (-3)
+#define GD_ERR_NON_RGB (-4) /* reference: "For non-RGB, provide precomputed Gaussian colors!" */
+
+typedef struct CUstream_st* gd_stream_t; /* == cudaStream_t */
+
+/* One camera view (reference: GaussianRasterizationSettings, DGR/diff_gaussian_rasterization/__init__.py:160-172). */
+typedef struct {
+  const float* viewmatrix; /* [16] device */
+  const float* projmatrix; /* [16] device */
+  const float* campos;     /* [3]  device */
+  float tanfovx, tanfovy;
+} GdView;
+
+/* Device-side counters written by gd_raster_forward (copy back when needed). */
+typedef struct {
+  uint32_t num_rendered; /* total (Gaussian, tile) instances over all B views */
+  uint32_t overflow;     /* 1 if num_rendered > max_rendered: outputs are blank, re-run bigger */
+  uint32_t view_base[GD_MAX_VIEWS + 1]; /* first instance of each view in the global list */
+} GdCounters;
+
+typedef struct {
+  int P, D, M;  /* Gaussians, active SH degree, SH coefficients per Gaussian */
+  int W, H, B;  /* image width, height, number of views (1..GD_MAX_VIEWS) */
+  const float* background;     /* [3] */
+  const float* means3D;        /* [P,3] */
+  const float* shs;            /* [P,M,3] or NULL */
+  const float* colors_precomp; /* [P,3] or NULL (exactly one of shs / colors_precomp) */
+  const float* opacities;      /* [P] */
+  const float* scales;         /* [P,3] or NULL */
+  float scale_modifier;
+  const float* rotations;      /* [P,4] or NULL */
+  const float* cov3D_precomp;  /* [P,6] or NULL (exactly one of scales+rotations / cov3D) */
+  GdView views[GD_MAX_VIEWS];
+  int prefiltered; /* accepted for API compatibility; culled points are skipped either way */
+  int debug;       /* non-zero: synchronise after the call and report CUDA errors (CHECK_CUDA) */
+  /* outputs */
+  float* out_color; /* [B,3,H,W] */
+  float* out_depth; /* [B,1,H,W] */
+  float* out_alpha; /* [B,1,H,W] */
+  int* radii;       /* [B,P] */
+  /* caller-owned state, sizes from gd_raster_state_bytes; must survive until backward */
+  void* geom_buffer;    size_t geom_bytes;
+  void* binning_buffer; size_t binning_bytes;
+  void* img_buffer;     size_t img_bytes;
+  uint32_t max_rendered; /* capacity of the instance arena the binning buffer was sized for */
+} GdFwdArgs;
+
+typedef struct {
+  int P, D, M, W, H, B;
+  const float* background;
+  const float* means3D;
+  const float* shs;
+  const float* colors_precomp;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* cov3D_precomp;
+  GdView views[GD_MAX_VIEWS];
+  const int* radii;         /* [B,P] from forward */
+  const float* out_alpha;   /* [B,1,H,W] from forward */
+  const float* dL_dcolor;   /* [B,3,H,W] */
+  const float* dL_ddepth;   /* [B,1,H,W] */
+  const float* dL_dalpha;   /* [B,1,H,W] */
+  int debug;
+  /*
+   * Gradient outputs. Every element is WRITTEN (no zero-initialisation needed; Gaussians that
+   * were invisible in a view get exact zeros, like the reference's torch::zeros + skipped
+   * threads). sum_views = 0: per-view gradients, leading dimension B (B = 1 is the reference
+   * layout). sum_views = 1: gradients summed over the B views in view order (what autograd
+   * accumulates over the reference's per-view loop), leading dimension dropped.
+   */
+  int sum_views;
+  float* dL_dmeans2D;   /* [B,P,3]  (grad wrt NDC position; z = 0) */
+  float* dL_dcolors;    /* [B,P,3]  */
+  float* dL_dopacity;   /* [B,P]    */
+  float* dL_dmeans3D;   /* [B,P,3]  */
+  float* dL_dcov3D;     /* [B,P,6]  */
+  float* dL_dsh;        /* [B,P,M,3] or NULL when shs == NULL */
+  float* dL_dscales;    /* [B,P,3]  or NULL when scales == NULL */
+  float* dL_drotations; /* [B,P,4]  or NULL when scales == NULL */
+  float* dL_dconic;     /* [B,P,4] optional (NULL to skip): slots x,y,w used, z = 0 */
+  float* dL_ddepths;    /* [B,P]   optional (NULL to skip) */
+  void* geom_buffer;    size_t geom_bytes;
+  void* binning_buffer; size_t binning_bytes;
+  void* img_buffer;     size_t img_bytes;
+  uint32_t max_rendered;
+} GdBwdArgs;
+
+/* Read-only device pointers into the state buffers (parity tests, debugging). */
+typedef struct {
+  const float* records;           /* [B*P,12]: conic.xyz, opacity | px, py, depth, r | g, b, -, - */
+  const uint32_t* tiles_touched;  /* [B*P] */
+  const uint32_t* point_offsets;  /* [B*P] inclusive scan over the view-major concatenation */
+  const float* cov3D;             /* [P,6] */
+  const uint8_t* clamped;         /* [B*P] bit k = colour channel k was clamped */
+  const GdCounters* counters;
+  const uint32_t* point_list;     /* [num_rendered] Gaussian index, sorted by (view, tile, depth, index) */
+  const uint64_t* tile_keys;      /* [num_rendered] (depth_bits << 32 | index), sorted per tile */
+  const float* sorted_records;    /* [num_rendered,12] records gathered in sorted order */
+  const uint32_t* instance_slot;  /* [num_rendered] unsorted instance -> sorted position */
+  const float* instance_grad;     /* [num_rendered,12] written by backward */
+  const uint32_t* ranges;         /* [B*T,2] global [start,end) per tile; (0,0) if empty */
+  const uint32_t* n_contrib;      /* [B*H*W] */
+} GdStateView;
+
+/* Bytes needed for the three state buffers. */
+int gd_raster_state_bytes(int P, int W, int H, int B, uint32_t max_rendered, size_t* geom_bytes,
+                          size_t* binning_bytes, size_t* img_bytes);
+int gd_raster_state_view(int P, int W, int H, int B, uint32_t max_rendered, void* geom_buffer,
+                         void* binning_buffer, void* img_buffer, GdStateView* out);
+
+/* Asynchronous on `stream`; returns GD_OK or a negative error code. */
+int gd_raster_forward(const GdFwdArgs* args, gd_stream_t stream);
+int gd_raster_backward(const GdBwdArgs* args, gd_stream_t stream);
+/* present[i] = (view-space z of means3D[i]) > 0.2 */
+int gd_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, gd_stream_t stream);
+
+const char* gd_last_error(void);
+/* Number of kernels this library has launched so far in this process (bench.py gpu_launches). */
+uint64_t gd_launch_count(void);
+const char* gd_raster_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GD_RASTER_H_ */
