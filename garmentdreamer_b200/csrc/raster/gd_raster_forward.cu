@@ -543,25 +543,30 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
     const int slot = c % kFwdStages;
     mbar_wait(&s_bar[slot], (uint32_t)((c / kFwdStages) & 1));
     const int cnt = min(kFwdChunk, n - c * kFwdChunk);
-    if (!done) {
+    {
+      // Branch-free body + __syncwarp keeps the 32 pixels of a warp converged: with `continue`
+      // in the loop the lanes drift apart and the warp issues each lane group separately.
       const float4* r = s_rec[slot];
       for (int j = 0; j < cnt; j++) {
+        if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // whole warp finished
         const float4 A = r[3 * j], Bq = r[3 * j + 1];
         const float dx = __fsub_rn(Bq.x, pfx), dy = __fsub_rn(Bq.y, pfy);
         const float power = pair_power(dx, dy, A.x, A.y, A.z);
-        if (power > 0.0f) continue;
         const float alpha = fminf(0.99f, __fmul_rn(A.w, expf(power)));
-        if (alpha < 1.0f / 255.0f) continue;
         const float test_T = __fmul_rn(Tr, __fsub_rn(1.0f, alpha));
-        if (test_T < 0.0001f) { done = true; break; }
-        const float4 Cq = r[3 * j + 2];
-        C0 = __fmaf_rn(Tr, __fmul_rn(alpha, Bq.w), C0);
-        C1 = __fmaf_rn(Tr, __fmul_rn(alpha, Cq.x), C1);
-        C2 = __fmaf_rn(Tr, __fmul_rn(alpha, Cq.y), C2);
-        weight = __fmaf_rn(Tr, alpha, weight);
-        Dp = __fmaf_rn(Tr, __fmul_rn(alpha, Bq.z), Dp);
-        Tr = test_T;
-        last_contributor = (uint32_t)(c * kFwdChunk + j + 1);
+        bool valid = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+        if (valid && test_T < 0.0001f) { done = true; valid = false; }
+        if (valid) {
+          const float4 Cq = r[3 * j + 2];
+          C0 = __fmaf_rn(Tr, __fmul_rn(alpha, Bq.w), C0);
+          C1 = __fmaf_rn(Tr, __fmul_rn(alpha, Cq.x), C1);
+          C2 = __fmaf_rn(Tr, __fmul_rn(alpha, Cq.y), C2);
+          weight = __fmaf_rn(Tr, alpha, weight);
+          Dp = __fmaf_rn(Tr, __fmul_rn(alpha, Bq.z), Dp);
+          Tr = test_T;
+          last_contributor = (uint32_t)(c * kFwdChunk + j + 1);
+        }
+        __syncwarp();
       }
     }
     const int ndone = __syncthreads_count(done);  // also orders slot reuse after all reads

@@ -180,7 +180,7 @@ def forward_views(means3D, opacities, views: Sequence[View], W: int, H: int, bg,
 def backward_views(state: RasterState, means3D, radii, out_alpha, bg, dL_dcolor, dL_ddepth,
                    dL_dalpha, *, shs=None, colors_precomp=None, scales=None, rotations=None,
                    cov3D_precomp=None, scale_modifier=1.0, sum_views=False, debug=False,
-                   want_aux=False):
+                   want_aux=False, out=None):
     """Returns a dict of gradients; leading dim B unless sum_views (reference order of
     rasterize_points.cu:207: means2D, colors, opacity, means3D, cov3D, sh, scales, rotations)."""
     lib = _lib.raster_lib()
@@ -198,6 +198,10 @@ def backward_views(state: RasterState, means3D, radii, out_alpha, bg, dL_dcolor,
         "cov3D": torch.empty(lead + (P, 6), **f), "sh": torch.empty(lead + (P, M, 3), **f),
         "scales": torch.empty(lead + (P, 3), **f), "rotations": torch.empty(lead + (P, 4), **f),
     }
+    if out:  # caller-provided destinations (e.g. slices of one flat all-reduce buffer)
+        for k, v in out.items():
+            assert v.is_contiguous() and v.dtype == torch.float32 and v.numel() == g[k].numel(), k
+            g[k] = v
     if shs is None:
         g["sh"].zero_()
     if scales is None:
