@@ -1,0 +1,267 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (fp16 in, fp32 accumulate).
+//
+// One CTA per 128 x BLOCK_N output tile, 192 threads, warp-specialised:
+//   warp 0    : TMA producer  -- cp.async.bulk.tensor (4-D box for A, 3-D box for B, 128B swizzle)
+//   warp 1    : MMA issuer    -- one elected lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16);
+//                                also owns the TMEM allocation
+//   warps 2-5 : epilogue      -- tcgen05.ld (32 lanes x 32 columns per warp), bias / time-embedding /
+//                                residual / SiLU / GEGLU / scale, fp16 stores
+// smem ring of kStages {A 128x64, B BLOCK_Nx64} fp16 tiles; full/empty mbarriers between producer
+// and issuer, tcgen05.commit releases slots and signals the epilogue.
+//
+// The A operand is addressed through a 4-D tensor map so that the same kernel runs
+//   * Linear layers and attention matmuls  (box 64 x 128 x 1 x 1, batched through d2), and
+//   * 3x3 / 1x1 convolutions as implicit GEMM over NHWC activations: for tap (dx,dy) the box
+//     {64 ch, W, rows, images} is fetched at pixel offset (dx,dy); TMA zero-fills out-of-bounds
+//     pixels, which implements the padding. K runs over (tap, channel-block).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gd_unet.h"
+
+namespace gdu {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;   // 64 fp16 = 128 bytes = one swizzle row
+constexpr int kGemmThreads = 192;
+
+struct GemmKParams {
+  int M, N, num_kb, kb_per_tap;
+  int mode_conv;  // 0: A coords {k, m0, z, 0};  1: conv taps
+  int tap_dx[9], tap_dy[9], tap_c[9];
+  int rows_per_image, img_w, rows_box, imgs_box;  // conv tile = imgs_box x rows_box x img_w pixels
+  int heads, a_head_k, a_zflat, b_head_k, b_head_n, b_zdim;
+  __half* C;
+  long long ldc, c_batch_stride, c_head_stride;
+  const __half* bias;
+  const __half* row_bias;
+  const __half* residual;
+  float alpha;
+  unsigned flags;
+  int block_n;
+  int stages;
+};
+
+__device__ __forceinline__ uint32_t s2u(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(n));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(s2u(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart): UMMA smem
+// descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO 1 | SBO 1024>>4 | version 1 | SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, F16 x F16, K-major A and B.
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = p.block_n, S = p.stages;
+  const uint32_t a_bytes = kBM * kBK * 2, b_bytes = (uint32_t)BN * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* empty = full + S;
+  uint64_t* tmem_full = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, n_blk = blockIdx.y, z = blockIdx.z;
+  const int zh = z % p.heads, zb = z / p.heads;
+  const uint32_t tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < S; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+    bar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      int a_c1, a_c2, a_c3;
+      if (p.mode_conv) {
+        const int tile_rows = p.rows_box * p.img_w;             // pixels per image in this tile
+        const int tiles_per_img = p.rows_per_image / tile_rows; // >= 1 when imgs_box == 1
+        if (p.imgs_box == 1) { a_c3 = m_blk / tiles_per_img; a_c2 = (m_blk % tiles_per_img) * p.rows_box; }
+        else { a_c3 = m_blk * p.imgs_box; a_c2 = 0; }
+        a_c1 = 0;
+      } else {
+        a_c1 = m_blk * kBM; a_c2 = p.a_zflat ? z : zb; a_c3 = 0;
+      }
+      const int b_c1 = n_blk * BN + zh * p.b_head_n;
+      for (int kb = 0; kb < p.num_kb; kb++) {
+        const int s = kb % S;
+        bar_wait(&empty[s], ((kb / S) & 1) ^ 1);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        bar_expect_tx(&full[s], a_bytes + b_bytes);
+        if (p.mode_conv) {
+          const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
+          tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+        } else {
+          tma_load_4d(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
+        }
+        tma_load_3d(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, p.b_zdim > 1 ? zb : 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = umma_idesc_f16(BN);
+    for (int kb = 0; kb < p.num_kb; kb++) {
+      const int s = kb % S;
+      bar_wait(&full[s], (kb / S) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; k++)  // +32 B per K=16 step inside the 128 B swizzle row
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&empty[s]);                       // slot free once these MMAs have read it
+        if (kb == p.num_kb - 1) umma_commit(tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) ----------------
+    const int q = warp & 3;
+    bar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m_blk * kBM + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;
+    const int img = p.rows_per_image > 0 ? row / p.rows_per_image : 0;
+    const bool geglu = p.flags & GD_EPI_GEGLU, transposed = p.flags & GD_EPI_TRANSPOSED;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n0 = n_blk * BN + c0;
+      if (!row_ok || n0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int n = n0 + j;
+        float x = __uint_as_float(r[j]) * p.alpha;
+        if (n < p.N) {
+          if (p.bias) x += __half2float(p.bias[n]);
+          if (p.row_bias) x += __half2float(p.row_bias[(long long)img * p.N + n]);
+        }
+        v[j] = x;
+      }
+      if (geglu) {  // columns come as 16 values followed by their 16 gates
+        __half* dst = p.C + coff + (long long)row * p.ldc + (n0 >> 1);
+        __align__(16) __half o[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) o[j] = __float2half_rn(v[j] * gelu_erf(v[16 + j]));
+        if (n0 + 32 <= p.N) {
+          reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
+          reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
+        }
+      } else if (transposed) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n = n0 + j;
+          if (n < p.N) p.C[coff + (long long)n * p.ldc + row] = __float2half_rn(v[j]);
+        }
+      } else {
+        __half* dst = p.C + coff + (long long)row * p.ldc + n0;
+        const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
+        if (n0 + 32 <= p.N && (p.ldc & 7) == 0) {
+          __align__(16) __half o[32];
+          if (res) {
+            __align__(16) __half rr[32];
+#pragma unroll
+            for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(rr)[u] = reinterpret_cast<const uint4*>(res)[u];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] += __half2float(rr[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j++) o[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(v[j]) : v[j]);
+#pragma unroll
+          for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
+        } else {
+          for (int j = 0; j < 32; j++) {
+            if (n0 + j < p.N) {
+              float x = v[j] + (res ? __half2float(res[j]) : 0.0f);
+              dst[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(x) : x);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+}  // namespace gdu

@@ -1,0 +1,511 @@
+// Host side of include/gd_unet.h + the small fused kernels around the tcgen05 GEMM.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "gd_gemm.cuh"
+
+namespace {
+thread_local char g_err[512] = {0};
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return GD_UNET_ERR_CUDA;
+  }
+  return GD_UNET_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+             const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GD_UNET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return GD_UNET_ERR_CUDA;
+  }
+  return GD_UNET_OK;
+}
+#define LAUNCH_CHECK(what)              \
+  do {                                  \
+    const int rc_ = check_launch(what); \
+    if (rc_ != GD_UNET_OK) return rc_;  \
+  } while (0)
+}  // namespace
+
+namespace gdu {
+
+// ---- GroupNorm (+SiLU), NHWC fp16: one CTA per (image, group) -----------------------------
+__global__ void __launch_bounds__(256)
+k_groupnorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
+            const __half* __restrict__ beta, int HW, int C, int groups, float eps, int do_silu) {
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = C / groups, cp2 = cpg >> 1;  // cpg is even for every SD layer
+  const __half2* xb = reinterpret_cast<const __half2*>(x + (size_t)n * HW * C + (size_t)g * cpg);
+  __half2* yb = reinterpret_cast<__half2*>(y + (size_t)n * HW * C + (size_t)g * cpg);
+  const int total = HW * cp2;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / cp2, c = i % cp2;
+    const float2 v = __half22float2(xb[(size_t)pix * (C >> 1) + c]);
+    s += v.x + v.y;
+    ss += v.x * v.x + v.y * v.y;
+  }
+  __shared__ float sh[2][8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  s = 0.f; ss = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { s += sh[0][w]; ss += sh[1][w]; }
+  const float inv_n = 1.0f / (float)(HW * cpg);
+  const float mean = s * inv_n;
+  const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + eps);
+  const __half2* g2 = reinterpret_cast<const __half2*>(gamma + (size_t)g * cpg);
+  const __half2* b2 = reinterpret_cast<const __half2*>(beta + (size_t)g * cpg);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / cp2, c = i % cp2;
+    const float2 v = __half22float2(xb[(size_t)pix * (C >> 1) + c]);
+    const float2 ga = __half22float2(g2[c]), be = __half22float2(b2[c]);
+    float a = (v.x - mean) * rstd * ga.x + be.x, b = (v.y - mean) * rstd * ga.y + be.y;
+    if (do_silu) { a = silu(a); b = silu(b); }
+    yb[(size_t)pix * (C >> 1) + c] = __floats2half2_rn(a, b);
+  }
+}
+
+// ---- LayerNorm: one warp per row -----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_layernorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
+            const __half* __restrict__ beta, int rows, int C, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)row * C);
+  __half2* yr = reinterpret_cast<__half2*>(y + (size_t)row * C);
+  float s = 0.f, ss = 0.f;
+  for (int c = lane; c < (C >> 1); c += 32) {
+    const float2 v = __half22float2(xr[c]);
+    s += v.x + v.y; ss += v.x * v.x + v.y * v.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
+  const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+  const __half2* g2 = reinterpret_cast<const __half2*>(gamma);
+  const __half2* b2 = reinterpret_cast<const __half2*>(beta);
+  for (int c = lane; c < (C >> 1); c += 32) {
+    const float2 v = __half22float2(xr[c]), ga = __half22float2(g2[c]), be = __half22float2(b2[c]);
+    yr[c] = __floats2half2_rn((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y);
+  }
+}
+
+// ---- row softmax in place: one warp per row (cols <= 4096) ---------------------------------
+__global__ void __launch_bounds__(256)
+k_softmax(__half* __restrict__ s, long long rows, int cols, long long ld) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  __half* r = s + row * ld;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, __half2float(r[c]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(~0u, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += __expf(__half2float(r[c]) - mx);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(~0u, sum, o);
+  const float inv = 1.0f / sum;
+  for (int c = lane; c < cols; c += 32) r[c] = __float2half_rn(__expf(__half2float(r[c]) - mx) * inv);
+}
+
+__global__ void k_geglu(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const long long r = i / H;
+  const int j = (int)(i % H);
+  const float a = __half2float(x[r * 2 * H + j]), g = __half2float(x[r * 2 * H + H + j]);
+  y[i] = __float2half_rn(a * gelu_erf(g));
+}
+__global__ void k_add(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ y, long long n2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2) y[i] = __hadd2(a[i], b[i]);
+}
+__global__ void k_upsample2x(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * 2 * H * 2 * W * C8;
+  if (i >= total) return;
+  const int c = (int)(i % C8);
+  long long p = i / C8;
+  const int ox = (int)(p % (2 * W)); p /= 2 * W;
+  const int oy = (int)(p % (2 * H));
+  const int n = (int)(p / (2 * H));
+  y[i] = x[(((long long)n * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c];
+}
+__global__ void k_space_to_depth(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * H * W * C8;
+  if (i >= total) return;
+  const int c = (int)(i % C8);
+  long long p = i / C8;
+  const int ix = (int)(p % W); p /= W;
+  const int iy = (int)(p % H);
+  const int n = (int)(p / H);
+  const int ph = (iy & 1) * 2 + (ix & 1);
+  y[((((long long)n * (H >> 1) + (iy >> 1)) * (W >> 1) + (ix >> 1)) * 4 + ph) * C8 + c] = x[i];
+}
+__global__ void k_concat(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long long rows,
+                         int Ca8, int Cb8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Ct = Ca8 + Cb8;
+  if (i >= rows * Ct) return;
+  const long long r = i / Ct;
+  const int c = (int)(i % Ct);
+  y[i] = c < Ca8 ? a[r * Ca8 + c] : b[r * Cb8 + (c - Ca8)];
+}
+// y[b,n] = act_out(bias[n] + sum_k act_in(x[b,k]) W[n,k]); one warp per output column n.
+__global__ void __launch_bounds__(256)
+k_small_linear(const __half* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ bias,
+               __half* __restrict__ y, int Bm, int K, int N, int silu_in, int silu_out) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int b = 0; b < 16; b++) acc[b] = 0.f;
+  const __half2* w2 = reinterpret_cast<const __half2*>(W + (size_t)n * K);
+  for (int k = lane; k < (K >> 1); k += 32) {
+    const float2 w = __half22float2(w2[k]);
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      if (b < Bm) {
+        float2 v = __half22float2(reinterpret_cast<const __half2*>(x + (size_t)b * K)[k]);
+        if (silu_in) { v.x = silu(v.x); v.y = silu(v.y); }
+        acc[b] += v.x * w.x + v.y * w.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[b] += __shfl_xor_sync(~0u, acc[b], o);
+  }
+  if (lane == 0) {
+    const float bv = bias ? __half2float(bias[n]) : 0.f;
+    for (int b = 0; b < Bm; b++) {
+      float v = acc[b] + bv;
+      if (silu_out) v = silu(v);
+      y[(size_t)b * N + n] = __float2half_rn(v);
+    }
+  }
+}
+__global__ void k_timestep_embedding(const float* __restrict__ t, __half* __restrict__ y, int Bm, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim >> 1;
+  if (i >= Bm * half) return;
+  const int b = i / half, k = i % half;
+  const float tt = __half2float(__float2half_rn(t[b]));  // reference casts t to fp16 first
+  const float freq = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float a = tt * freq;
+  y[(size_t)b * dim + k] = __float2half_rn(cosf(a));         // flip_sin_to_cos: [cos | sin]
+  y[(size_t)b * dim + half + k] = __float2half_rn(sinf(a));
+}
+// conv_in: Cin = 4, NCHW fp16 in -> NHWC fp16 out. One thread per (pixel, 8 output channels).
+__global__ void __launch_bounds__(256)
+k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+          __half* __restrict__ y, int N, int H, int W, int Cout) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C8 = Cout >> 3;
+  if (i >= (long long)N * H * W * C8) return;
+  const int cg = (int)(i % C8);
+  long long p = i / C8;
+  const int px = (int)(p % W); p /= W;
+  const int py = (int)(p % H);
+  const int n = (int)(p / H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = __half2float(bias[cg * 8 + j]);
+  for (int ky = 0; ky < 3; ky++) {
+    const int iy = py + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; kx++) {
+      const int ix = px + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      float in[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) in[c] = __half2float(x[(((size_t)n * 4 + c) * H + iy) * W + ix]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const __half* wp = w + (((size_t)(cg * 8 + j) * 3 + ky) * 3 + kx) * 4;
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[j] += in[c] * __half2float(wp[c]);
+      }
+    }
+  }
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) o[j] = __float2half_rn(acc[j]);
+  *reinterpret_cast<uint4*>(y + (((size_t)n * H + py) * W + px) * Cout + cg * 8) = *reinterpret_cast<const uint4*>(o);
+}
+// conv_out: Cout = 4, NHWC fp16 in -> NCHW fp32 out. One warp per pixel.
+__global__ void __launch_bounds__(256)
+k_conv_out(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+           float* __restrict__ y, int N, int H, int W, int Cin) {
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)N * H * W) return;
+  const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ky = 0; ky < 3; ky++) {
+    const int iy = py + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; kx++) {
+      const int ix = px + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      const __half2* xp = reinterpret_cast<const __half2*>(x + (((size_t)n * H + iy) * W + ix) * Cin);
+      for (int c = lane; c < (Cin >> 1); c += 32) {
+        const float2 v = __half22float2(xp[c]);
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          const float2 ww = __half22float2(reinterpret_cast<const __half2*>(w + (((size_t)o * 3 + ky) * 3 + kx) * Cin)[c]);
+          acc[o] += v.x * ww.x + v.y * ww.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; o++) {
+#pragma unroll
+    for (int s = 16; s; s >>= 1) acc[o] += __shfl_xor_sync(~0u, acc[o], s);
+  }
+  if (lane < 4) {
+    float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+    // the reference UNet runs in fp16: its conv_out result is rounded to fp16 before .to(fp32)
+    v = __half2float(__float2half_rn(v + __half2float(bias[lane])));
+    y[(((size_t)n * 4 + lane) * H + py) * W + px] = v;
+  }
+}
+__global__ void k_add_noise(const float* __restrict__ lat, const float* __restrict__ noise, const float* __restrict__ sa,
+                            const float* __restrict__ sb, float* __restrict__ noisy, __half* __restrict__ uin, int B,
+                            int reps, int chw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * chw) return;
+  const int b = i / chw;
+  const float v = sa[b] * lat[i] + sb[b] * noise[i];
+  noisy[i] = v;
+  const __half h = __float2half_rn(v);
+  for (int r = 0; r < reps; r++) uin[(size_t)r * B * chw + i] = h;
+}
+__global__ void k_sds_grad(const float* __restrict__ eps, const float* __restrict__ noise, const float* __restrict__ w,
+                           float s, float* __restrict__ noise_pred, float* __restrict__ grad, int B, int chw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * chw) return;
+  const int b = i / chw;
+  const float et = eps[i], eu = eps[(size_t)B * chw + i];
+  const float np = et + s * (et - eu);  // sic: base term is e_text (stable_diffusion_guidance.py:248-251)
+  if (noise_pred) noise_pred[i] = np;
+  grad[i] = w[b] * (np - noise[i]);
+}
+
+}  // namespace gdu
+
+extern "C" {
+
+const char* gd_unet_last_error(void) { return g_err; }
+uint64_t gd_unet_launch_count(void) { return g_launches.load(); }
+const char* gd_unet_version(void) { return "gd_unet 0.1 (sm_100a, tcgen05+TMA)"; }
+
+int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->A || !a->B || !a->C) return fail(GD_UNET_ERR_INVALID_ARG, "gemm: null pointer");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || a->K % gdu::kBK) return fail(GD_UNET_ERR_INVALID_ARG, "gemm: K must be a positive multiple of 64");
+  if (a->batch < 1 || a->heads < 1 || a->batch % a->heads) return fail(GD_UNET_ERR_INVALID_ARG, "gemm: bad batch/heads");
+  if (a->a_box[0] != gdu::kBK || a->a_box[1] * a->a_box[2] * a->a_box[3] != gdu::kBM)
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: A box must be 64 x (128 rows)");
+  const int ntaps = a->ntaps > 0 ? a->ntaps : 1;
+  if (ntaps > 9 || (a->ntaps > 0 && (a->Ck <= 0 || a->Ck % gdu::kBK || a->K != ntaps * a->Ck)))
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: bad tap description");
+  if ((a->flags & GD_EPI_GEGLU) && (a->N % 32 || (a->flags & GD_EPI_TRANSPOSED) || a->residual))
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: GEGLU epilogue needs N % 32 == 0 and no residual/transposition");
+  int BN = a->block_n;
+  if (BN <= 0) {
+    if (a->N <= 256) BN = (a->N + 15) / 16 * 16;
+    else {
+      const int cands[] = {256, 192, 160, 128};
+      BN = 128;
+      for (int c : cands) if (a->N % c == 0) { BN = c; break; }
+    }
+  }
+  if (BN % 16 || BN < 16 || BN > 256 || ((a->flags & GD_EPI_GEGLU) && BN % 32))
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: block_n must be a multiple of 16 in 16..256");
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->a_dim[0], (cuuint64_t)a->a_dim[1], (cuuint64_t)a->a_dim[2], (cuuint64_t)a->a_dim[3]};
+    cuuint64_t str[3] = {(cuuint64_t)a->a_stride[0], (cuuint64_t)a->a_stride[1], (cuuint64_t)a->a_stride[2]};
+    cuuint32_t box[4] = {(cuuint32_t)a->a_box[0], (cuuint32_t)a->a_box[1], (cuuint32_t)a->a_box[2], (cuuint32_t)a->a_box[3]};
+    const int rc = make_map(&tmA, a->A, 4, dims, str, box);
+    if (rc != GD_UNET_OK) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a->b_dim[0], (cuuint64_t)a->b_dim[1], (cuuint64_t)a->b_dim[2]};
+    cuuint64_t str[2] = {(cuuint64_t)a->b_stride[0], (cuuint64_t)a->b_stride[1]};
+    cuuint32_t box[3] = {(cuuint32_t)gdu::kBK, (cuuint32_t)BN, 1};
+    const int rc = make_map(&tmB, a->B, 3, dims, str, box);
+    if (rc != GD_UNET_OK) return rc;
+  }
+  gdu::GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.num_kb = a->K / gdu::kBK;
+  p.mode_conv = a->ntaps > 0 ? 1 : 0;
+  p.kb_per_tap = p.mode_conv ? a->Ck / gdu::kBK : p.num_kb;
+  for (int t = 0; t < 9; t++) { p.tap_dx[t] = a->tap_dx[t]; p.tap_dy[t] = a->tap_dy[t]; p.tap_c[t] = a->tap_c[t]; }
+  p.rows_per_image = a->rows_per_image; p.img_w = a->img_w;
+  p.rows_box = a->a_box[2]; p.imgs_box = a->a_box[3];
+  if (p.mode_conv) {
+    if (a->a_box[1] != a->img_w || a->rows_per_image != a->img_w * a->img_h || a->img_h % a->a_box[2])
+      return fail(GD_UNET_ERR_INVALID_ARG, "gemm: conv box must span full image rows");
+    if (a->a_box[3] > 1 && a->a_box[2] != a->img_h) return fail(GD_UNET_ERR_INVALID_ARG, "gemm: multi-image box must hold whole images");
+  }
+  p.heads = a->heads; p.a_head_k = a->a_head_k; p.a_zflat = a->a_zflat; p.b_head_k = a->b_head_k; p.b_head_n = a->b_head_n; p.b_zdim = a->b_dim[2];
+  p.C = reinterpret_cast<__half*>(a->C); p.ldc = a->ldc; p.c_batch_stride = a->c_batch_stride; p.c_head_stride = a->c_head_stride;
+  p.bias = reinterpret_cast<const __half*>(a->bias); p.row_bias = reinterpret_cast<const __half*>(a->row_bias);
+  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
+  const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gdu::k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
+    attr_set = true;
+  }
+  dim3 grid((a->M + gdu::kBM - 1) / gdu::kBM, (a->N + BN - 1) / BN, a->batch);
+  gdu::k_gemm_tcgen05<<<grid, gdu::kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  LAUNCH_CHECK("k_gemm_tcgen05");
+  return GD_UNET_OK;
+}
+
+int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int N, int HW, int C, int groups,
+                      float eps, int silu, gd_ustream_t s) {
+  if (C % groups || (C / groups) % 2) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm: channels per group must be even");
+  gdu::k_groupnorm<<<N * groups, 256, 0, (cudaStream_t)s>>>((const __half*)x, (__half*)y, (const __half*)gamma,
+                                                           (const __half*)beta, HW, C, groups, eps, silu);
+  LAUNCH_CHECK("k_groupnorm");
+  return GD_UNET_OK;
+}
+int gd_unet_layernorm(const void* x, void* y, const void* gamma, const void* beta, int rows, int C, float eps, gd_ustream_t s) {
+  if (C % 2) return fail(GD_UNET_ERR_INVALID_ARG, "layernorm: C must be even");
+  gdu::k_layernorm<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>((const __half*)x, (__half*)y, (const __half*)gamma,
+                                                               (const __half*)beta, rows, C, eps);
+  LAUNCH_CHECK("k_layernorm");
+  return GD_UNET_OK;
+}
+int gd_unet_softmax(void* sc, long long rows, int cols, long long ld, gd_ustream_t s) {
+  gdu::k_softmax<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)s>>>((__half*)sc, rows, cols, ld);
+  LAUNCH_CHECK("k_softmax");
+  return GD_UNET_OK;
+}
+int gd_unet_geglu(const void* x, void* y, long long rows, int H, gd_ustream_t s) {
+  gdu::k_geglu<<<(unsigned)((rows * H + 255) / 256), 256, 0, (cudaStream_t)s>>>((const __half*)x, (__half*)y, rows, H);
+  LAUNCH_CHECK("k_geglu");
+  return GD_UNET_OK;
+}
+int gd_unet_add(const void* a, const void* b, void* y, long long n, gd_ustream_t s) {
+  if (n % 2) return fail(GD_UNET_ERR_INVALID_ARG, "add: n must be even");
+  gdu::k_add<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)s>>>((const __half2*)a, (const __half2*)b, (__half2*)y, n / 2);
+  LAUNCH_CHECK("k_add");
+  return GD_UNET_OK;
+}
+int gd_unet_upsample2x(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t s) {
+  if (C % 8) return fail(GD_UNET_ERR_INVALID_ARG, "upsample: C % 8");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  gdu::k_upsample2x<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  LAUNCH_CHECK("k_upsample2x");
+  return GD_UNET_OK;
+}
+int gd_unet_space_to_depth(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t s) {
+  if (C % 8 || H % 2 || W % 2) return fail(GD_UNET_ERR_INVALID_ARG, "space_to_depth: C % 8, even H/W");
+  const long long total = (long long)N * H * W * (C / 8);
+  gdu::k_space_to_depth<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  LAUNCH_CHECK("k_space_to_depth");
+  return GD_UNET_OK;
+}
+int gd_unet_concat(const void* a, const void* b, void* y, long long rows, int Ca, int Cb, gd_ustream_t s) {
+  if (Ca % 8 || Cb % 8) return fail(GD_UNET_ERR_INVALID_ARG, "concat: C % 8");
+  const long long total = rows * ((Ca + Cb) / 8);
+  gdu::k_concat<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const uint4*)a, (const uint4*)b, (uint4*)y, rows, Ca / 8, Cb / 8);
+  LAUNCH_CHECK("k_concat");
+  return GD_UNET_OK;
+}
+int gd_unet_small_linear(const void* x, const void* W, const void* bias, void* y, int Bm, int K, int N, int silu_in,
+                         int silu_out, gd_ustream_t s) {
+  if (Bm < 1 || Bm > 16 || K % 2) return fail(GD_UNET_ERR_INVALID_ARG, "small_linear: 1 <= Bm <= 16, even K");
+  gdu::k_small_linear<<<(N + 7) / 8, 256, 0, (cudaStream_t)s>>>((const __half*)x, (const __half*)W, (const __half*)bias,
+                                                               (__half*)y, Bm, K, N, silu_in, silu_out);
+  LAUNCH_CHECK("k_small_linear");
+  return GD_UNET_OK;
+}
+int gd_unet_timestep_embedding(const float* t, void* y, int Bm, int dim, gd_ustream_t s) {
+  gdu::k_timestep_embedding<<<(Bm * dim / 2 + 127) / 128, 128, 0, (cudaStream_t)s>>>(t, (__half*)y, Bm, dim);
+  LAUNCH_CHECK("k_timestep_embedding");
+  return GD_UNET_OK;
+}
+int gd_unet_conv_in(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int Cout, gd_ustream_t s) {
+  if (Cout % 8) return fail(GD_UNET_ERR_INVALID_ARG, "conv_in: Cout % 8");
+  const long long total = (long long)N * H * W * (Cout / 8);
+  gdu::k_conv_in<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const __half*)x, (const __half*)w,
+                                                                              (const __half*)bias, (__half*)y, N, H, W, Cout);
+  LAUNCH_CHECK("k_conv_in");
+  return GD_UNET_OK;
+}
+int gd_unet_conv_out(const void* x, const void* w, const void* bias, float* y, int N, int H, int W, int Cin, gd_ustream_t s) {
+  const long long pix = (long long)N * H * W;
+  gdu::k_conv_out<<<(unsigned)((pix + 7) / 8), 256, 0, (cudaStream_t)s>>>((const __half*)x, (const __half*)w,
+                                                                         (const __half*)bias, y, N, H, W, Cin);
+  LAUNCH_CHECK("k_conv_out");
+  return GD_UNET_OK;
+}
+int gd_unet_add_noise(const float* lat, const float* noise, const float* sa, const float* sb, float* noisy, void* uin, int B,
+                      int reps, int chw, gd_ustream_t s) {
+  gdu::k_add_noise<<<(B * chw + 255) / 256, 256, 0, (cudaStream_t)s>>>(lat, noise, sa, sb, noisy, (__half*)uin, B, reps, chw);
+  LAUNCH_CHECK("k_add_noise");
+  return GD_UNET_OK;
+}
+int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float gs, float* np, float* grad, int B, int chw,
+                     gd_ustream_t s) {
+  gdu::k_sds_grad<<<(B * chw + 255) / 256, 256, 0, (cudaStream_t)s>>>(eps, noise, w, gs, np, grad, B, chw);
+  LAUNCH_CHECK("k_sds_grad");
+  return GD_UNET_OK;
+}
+
+}  // extern "C"

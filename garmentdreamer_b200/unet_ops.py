@@ -1,0 +1,354 @@
+"""Torch-facing wrappers of the UNet operator C ABI (include/gd_unet.h). fp16, channels-last.
+
+Every dense contraction goes through ONE kernel (gd_unet_gemm: tcgen05.mma + TMEM + TMA); the
+wrappers only describe the operand tensors (dims / strides / TMA boxes / conv taps).
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+EPI_SILU, EPI_TRANSPOSED, EPI_GEGLU = 1, 2, 4
+
+
+class GdGemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("batch", ctypes.c_int), ("heads", ctypes.c_int),
+        ("A", ctypes.c_void_p),
+        ("a_dim", ctypes.c_int * 4), ("a_stride", ctypes.c_longlong * 3), ("a_box", ctypes.c_int * 4),
+        ("ntaps", ctypes.c_int), ("Ck", ctypes.c_int),
+        ("tap_dx", ctypes.c_int * 9), ("tap_dy", ctypes.c_int * 9), ("tap_c", ctypes.c_int * 9),
+        ("rows_per_image", ctypes.c_int), ("img_w", ctypes.c_int), ("img_h", ctypes.c_int),
+        ("a_head_k", ctypes.c_int), ("a_zflat", ctypes.c_int),
+        ("B", ctypes.c_void_p),
+        ("b_dim", ctypes.c_int * 3), ("b_stride", ctypes.c_longlong * 2),
+        ("b_head_k", ctypes.c_int), ("b_head_n", ctypes.c_int),
+        ("C", ctypes.c_void_p),
+        ("ldc", ctypes.c_longlong), ("c_batch_stride", ctypes.c_longlong), ("c_head_stride", ctypes.c_longlong),
+        ("bias", ctypes.c_void_p), ("row_bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+        ("alpha", ctypes.c_float), ("flags", ctypes.c_uint), ("block_n", ctypes.c_int),
+    ]
+
+
+_unet = None
+
+
+def lib():
+    """libgd_unet.so; raises if it has not been built (no fallback path exists)."""
+    global _unet
+    if _unet is None:
+        path = os.path.join(_lib.LIB_DIR, "libgd_unet.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `make -C garmentdreamer_b200/csrc unet`. "
+                               "There is no CPU or library fallback.")
+        L = ctypes.CDLL(path)
+        L.gd_unet_last_error.restype = ctypes.c_char_p
+        L.gd_unet_version.restype = ctypes.c_char_p
+        L.gd_unet_launch_count.restype = ctypes.c_uint64
+        L.gd_unet_gemm.argtypes = [ctypes.POINTER(GdGemmArgs), ctypes.c_void_p]
+        vp, i, f, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+        L.gd_unet_groupnorm.argtypes = [vp, vp, vp, vp, i, i, i, i, f, i, vp]
+        L.gd_unet_layernorm.argtypes = [vp, vp, vp, vp, i, i, f, vp]
+        L.gd_unet_softmax.argtypes = [vp, ll, i, ll, vp]
+        L.gd_unet_geglu.argtypes = [vp, vp, ll, i, vp]
+        L.gd_unet_add.argtypes = [vp, vp, vp, ll, vp]
+        L.gd_unet_upsample2x.argtypes = [vp, vp, i, i, i, i, vp]
+        L.gd_unet_space_to_depth.argtypes = [vp, vp, i, i, i, i, vp]
+        L.gd_unet_concat.argtypes = [vp, vp, vp, ll, i, i, vp]
+        L.gd_unet_small_linear.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+        L.gd_unet_timestep_embedding.argtypes = [vp, vp, i, i, vp]
+        L.gd_unet_conv_in.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+        L.gd_unet_conv_out.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+        L.gd_unet_add_noise.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
+        L.gd_unet_sds_grad.argtypes = [vp, vp, vp, f, vp, vp, i, i, vp]
+        for name in ("gemm", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
+                     "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad"):
+            getattr(L, "gd_unet_" + name).restype = ctypes.c_int
+        _unet = L
+    return _unet
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().gd_unet_last_error().decode()}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _h(t):
+    assert t.dtype == torch.float16 and t.is_cuda and t.is_contiguous(), (t.dtype, t.device, t.is_contiguous())
+    return t
+
+
+def _gemm(a: GdGemmArgs):
+    _chk(lib().gd_unet_gemm(ctypes.byref(a), _stream()), "gd_unet_gemm")
+
+
+def linear(x, w, bias=None, *, residual=None, out=None, flags=0, alpha=1.0, block_n=0):
+    """y[M,N] = x[M,K] @ w[N,K]^T (+bias) (+residual); GEGLU flag halves N."""
+    _h(x); _h(w)
+    M, K = x.shape[-2] * (x.numel() // (x.shape[-1] * x.shape[-2])), x.shape[-1]
+    N = w.shape[0]
+    n_out = N // 2 if flags & EPI_GEGLU else N
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (n_out,), dtype=torch.float16, device=x.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = M, N, K, 1, 1
+    a.A = x.data_ptr()
+    a.a_dim[:] = [K, M, 1, 1]
+    a.a_stride[:] = [K * 2, M * K * 2, M * K * 2]
+    a.a_box[:] = [64, 128, 1, 1]
+    a.B = w.data_ptr()
+    a.b_dim[:] = [K, N, 1]
+    a.b_stride[:] = [K * 2, N * K * 2]
+    a.C, a.ldc = out.data_ptr(), n_out
+    a.bias, a.residual = _p(bias), _p(residual)
+    a.alpha, a.flags, a.block_n = alpha, flags, block_n
+    _gemm(a)
+    return out
+
+
+def _conv_box(H, W, N):
+    if W > 128 or 128 % W:
+        raise ValueError(f"conv width {W} must divide 128")
+    rows = 128 // W
+    if rows <= H:
+        if H % rows:
+            raise ValueError("conv height must be a multiple of the tile rows")
+        return W, rows, 1
+    if rows % H:
+        raise ValueError("conv tile must hold whole images")
+    return W, H, rows // H
+
+
+def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0):
+    """3x3, stride 1, pad 1 over NHWC x[N,H,W,Cin]; w[Cout,3,3,Cin]."""
+    _h(x); _h(w)
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=torch.float16, device=x.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = N * H * W, Cout, 9 * Cin, 1, 1
+    a.A = x.data_ptr()
+    a.a_dim[:] = [Cin, W, H, N]
+    a.a_stride[:] = [Cin * 2, W * Cin * 2, H * W * Cin * 2]
+    bw, bh, bn = _conv_box(H, W, N)
+    a.a_box[:] = [64, bw, bh, bn]
+    a.ntaps, a.Ck = 9, Cin
+    for t in range(9):
+        a.tap_dx[t], a.tap_dy[t], a.tap_c[t] = t % 3 - 1, t // 3 - 1, 0
+    a.rows_per_image, a.img_w, a.img_h = H * W, W, H
+    a.B = w.data_ptr()
+    a.b_dim[:] = [9 * Cin, Cout, 1]
+    a.b_stride[:] = [9 * Cin * 2, Cout * 9 * Cin * 2]
+    a.C, a.ldc = out.data_ptr(), Cout
+    a.bias, a.row_bias, a.residual = _p(bias), _p(row_bias), _p(residual)
+    a.alpha, a.flags = 1.0, flags
+    _gemm(a)
+    return out
+
+
+def conv3x3_stride2(x, w, bias=None, *, s2d=None, out=None):
+    """3x3, stride 2, pad 1 (diffusers Downsample2D): space-to-depth, then 9 taps with shifts in
+    {-1,0} over the 4 phase images (zero fill at the top/left border = the padding)."""
+    _h(x); _h(w)
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = H // 2, W // 2
+    if s2d is None:
+        s2d = torch.empty((N, Ho, Wo, 4 * Cin), dtype=torch.float16, device=x.device)
+    _chk(lib().gd_unet_space_to_depth(x.data_ptr(), s2d.data_ptr(), N, H, W, Cin, _stream()), "space_to_depth")
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float16, device=x.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = N * Ho * Wo, Cout, 9 * Cin, 1, 1
+    a.A = s2d.data_ptr()
+    a.a_dim[:] = [4 * Cin, Wo, Ho, N]
+    a.a_stride[:] = [4 * Cin * 2, Wo * 4 * Cin * 2, Ho * Wo * 4 * Cin * 2]
+    bw, bh, bn = _conv_box(Ho, Wo, N)
+    a.a_box[:] = [64, bw, bh, bn]
+    a.ntaps, a.Ck = 9, Cin
+    for t in range(9):
+        ky, kx = t // 3, t % 3
+        py, dy = (1, -1) if ky == 0 else ((0, 0) if ky == 1 else (1, 0))
+        px, dx = (1, -1) if kx == 0 else ((0, 0) if kx == 1 else (1, 0))
+        a.tap_dx[t], a.tap_dy[t], a.tap_c[t] = dx, dy, (py * 2 + px) * Cin
+    a.rows_per_image, a.img_w, a.img_h = Ho * Wo, Wo, Ho
+    a.B = w.data_ptr()
+    a.b_dim[:] = [9 * Cin, Cout, 1]
+    a.b_stride[:] = [9 * Cin * 2, Cout * 9 * Cin * 2]
+    a.C, a.ldc = out.data_ptr(), Cout
+    a.bias = _p(bias)
+    a.alpha = 1.0
+    _gemm(a)
+    return out
+
+
+def attn_scores(q, k, heads, scale, out=None):
+    """S[b,h] = scale * Q[b,:,h] K[b,:,h]^T ; q [B,Tq,C], k [B,Tk,C] -> S [B*heads,Tq,Tk] fp16."""
+    _h(q); _h(k)
+    B, Tq, C = q.shape
+    Tk = k.shape[1]
+    d = C // heads
+    assert d == 64, "head_dim 64 (SD-2.1)"
+    ld = (Tk + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((B * heads, Tq, ld), dtype=torch.float16, device=q.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = Tq, Tk, d, B * heads, heads
+    a.A = q.data_ptr()
+    a.a_dim[:] = [C, Tq, B, 1]
+    a.a_stride[:] = [C * 2, Tq * C * 2, B * Tq * C * 2]
+    a.a_box[:] = [64, 128, 1, 1]
+    a.a_head_k, a.a_zflat = d, 0
+    a.B = k.data_ptr()
+    a.b_dim[:] = [C, Tk, B]
+    a.b_stride[:] = [C * 2, Tk * C * 2]
+    a.b_head_k, a.b_head_n = d, 0
+    a.C, a.ldc = out.data_ptr(), ld
+    a.c_batch_stride, a.c_head_stride = heads * Tq * ld, Tq * ld
+    a.alpha = scale
+    _gemm(a)
+    return out
+
+
+def attn_values(p, vt, heads, Tk, out):
+    """O[b,:,h] = P[b,h] V[b,:,h]; p [B*heads,Tq,ld] (rows padded to ld), vt = V^T [B,C,ldv]."""
+    _h(p); _h(vt)
+    BH, Tq, ld = p.shape
+    B, C, ldv = vt.shape
+    d = C // heads
+    Kp = (Tk + 63) // 64 * 64  # K loop in 64-blocks; the tensor maps bound reads to Tk (zero fill)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = Tq, d, Kp, BH, heads
+    a.A = p.data_ptr()
+    a.a_dim[:] = [Tk, Tq, BH, 1]
+    a.a_stride[:] = [ld * 2, Tq * ld * 2, BH * Tq * ld * 2]
+    a.a_box[:] = [64, 128, 1, 1]
+    a.a_head_k, a.a_zflat = 0, 1
+    a.B = vt.data_ptr()
+    a.b_dim[:] = [Tk, C, B]
+    a.b_stride[:] = [ldv * 2, C * ldv * 2]
+    a.b_head_k, a.b_head_n = 0, d
+    a.C, a.ldc = out.data_ptr(), C
+    a.c_batch_stride, a.c_head_stride = Tq * C, d
+    a.alpha = 1.0
+    a.block_n = 64
+    _gemm(a)
+    return out
+
+
+def linear_transposed(x, w, Tk_pad, out=None):
+    """V^T projection: x [B,T,K] @ w[N,K]^T stored transposed per batch -> [B,N,Tk_pad]."""
+    _h(x); _h(w)
+    B, T, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.zeros((B, N, Tk_pad), dtype=torch.float16, device=x.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = T, N, K, B, 1
+    a.A = x.data_ptr()
+    a.a_dim[:] = [K, T, B, 1]
+    a.a_stride[:] = [K * 2, T * K * 2, B * T * K * 2]
+    a.a_box[:] = [64, 128, 1, 1]
+    a.B = w.data_ptr()
+    a.b_dim[:] = [K, N, 1]
+    a.b_stride[:] = [K * 2, N * K * 2]
+    a.C, a.ldc = out.data_ptr(), Tk_pad
+    a.c_batch_stride = N * Tk_pad
+    a.alpha, a.flags = 1.0, EPI_TRANSPOSED
+    _gemm(a)
+    return out
+
+
+def groupnorm(x, gamma, beta, groups=32, eps=1e-5, silu=False, out=None):
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    out = torch.empty_like(x) if out is None else out
+    _chk(lib().gd_unet_groupnorm(_h(x).data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, HW, C, groups,
+                                 eps, int(silu), _stream()), "groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    C = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    _chk(lib().gd_unet_layernorm(_h(x).data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                 x.numel() // C, C, eps, _stream()), "layernorm")
+    return out
+
+
+def softmax_(s, cols):
+    ld = s.shape[-1]
+    _chk(lib().gd_unet_softmax(_h(s).data_ptr(), s.numel() // ld, cols, ld, _stream()), "softmax")
+    return s
+
+
+def geglu(x, out=None):
+    H = x.shape[-1] // 2
+    out = torch.empty(x.shape[:-1] + (H,), dtype=torch.float16, device=x.device) if out is None else out
+    _chk(lib().gd_unet_geglu(_h(x).data_ptr(), out.data_ptr(), x.numel() // (2 * H), H, _stream()), "geglu")
+    return out
+
+
+def add(a, b, out=None):
+    out = torch.empty_like(a) if out is None else out
+    _chk(lib().gd_unet_add(_h(a).data_ptr(), _h(b).data_ptr(), out.data_ptr(), a.numel(), _stream()), "add")
+    return out
+
+
+def upsample2x(x, out=None):
+    N, H, W, C = x.shape
+    out = torch.empty((N, 2 * H, 2 * W, C), dtype=torch.float16, device=x.device) if out is None else out
+    _chk(lib().gd_unet_upsample2x(_h(x).data_ptr(), out.data_ptr(), N, H, W, C, _stream()), "upsample2x")
+    return out
+
+
+def concat(a, b, out=None):
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    out = torch.empty(a.shape[:-1] + (Ca + Cb,), dtype=torch.float16, device=a.device) if out is None else out
+    _chk(lib().gd_unet_concat(_h(a).data_ptr(), _h(b).data_ptr(), out.data_ptr(), a.numel() // Ca, Ca, Cb, _stream()), "concat")
+    return out
+
+
+def small_linear(x, w, bias, silu_in=False, silu_out=False):
+    Bm, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((Bm, N), dtype=torch.float16, device=x.device)
+    _chk(lib().gd_unet_small_linear(_h(x).data_ptr(), _h(w).data_ptr(), _p(bias), out.data_ptr(), Bm, K, N,
+                                    int(silu_in), int(silu_out), _stream()), "small_linear")
+    return out
+
+
+def timestep_embedding(t_f32, dim):
+    Bm = t_f32.shape[0]
+    out = torch.empty((Bm, dim), dtype=torch.float16, device=t_f32.device)
+    _chk(lib().gd_unet_timestep_embedding(t_f32.data_ptr(), out.data_ptr(), Bm, dim, _stream()), "timestep_embedding")
+    return out
+
+
+def conv_in(x_nchw, w, bias):
+    N, _, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    out = torch.empty((N, H, W, Cout), dtype=torch.float16, device=x_nchw.device)
+    _chk(lib().gd_unet_conv_in(_h(x_nchw).data_ptr(), _h(w).data_ptr(), bias.data_ptr(), out.data_ptr(), N, H, W, Cout,
+                               _stream()), "conv_in")
+    return out
+
+
+def conv_out(x, w, bias):
+    N, H, W, Cin = x.shape
+    out = torch.empty((N, 4, H, W), dtype=torch.float32, device=x.device)
+    _chk(lib().gd_unet_conv_out(_h(x).data_ptr(), _h(w).data_ptr(), bias.data_ptr(), out.data_ptr(), N, H, W, Cin,
+                                _stream()), "conv_out")
+    return out

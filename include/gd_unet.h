@@ -1,0 +1,126 @@
+/*
+ * gd_unet.h -- C ABI of the B200-native operators behind the Stable-Diffusion UNet step of
+ * StableDiffusionGuidance.compute_grad_sds
+ * (reference: Garment_3DGS/threestudio/models/guidance/stable_diffusion_guidance.py:146-157 and
+ * :185-276). The reference executes this step through diffusers 0.19.0 (not in the reference
+ * tree; requirements.txt:12) on torch / cuDNN / cuBLAS; here every dense contraction is ONE
+ * hand-written sm_100a kernel (tcgen05.mma with TMEM accumulators, operands staged by TMA) and
+ * the normalisation / activation / softmax / SDS epilogue steps are small fused CUDA kernels.
+ *
+ * All pointers are DEVICE pointers. Activations are fp16, channels-last: an image tensor is
+ * [N, H, W, C] and a token tensor is [rows, C]; weights are fp16 [N_out, K] (K contiguous),
+ * 3x3 convolution weights are [C_out, 3, 3, C_in]. Every call is asynchronous on `stream`
+ * and returns GD_UNET_OK or a negative error (message in gd_unet_last_error()).
+ */
+#ifndef GD_UNET_H_
+#define GD_UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_UNET_OK 0
+#define GD_UNET_ERR_INVALID_ARG (-1)
+#define GD_UNET_ERR_CUDA (-3)
+
+typedef struct CUstream_st* gd_ustream_t; /* == cudaStream_t */
+
+/* epilogue flags for gd_unet_gemm */
+#define GD_EPI_SILU 1u        /* y = silu(y) after bias */
+#define GD_EPI_TRANSPOSED 2u  /* store y^T (per batch): element (m,n) at C[n*ldc + m] */
+#define GD_EPI_GEGLU 4u       /* weight rows interleaved (value, gate) in blocks of 16: out[m, n/2] */
+
+typedef struct {
+  /* problem: C[z][M,N] (+)= A[z][M,K] * B[z][N,K]^T, fp16 in, fp32 accumulate, fp16 out */
+  int M, N, K;
+  int batch;          /* grid z (1 for plain layers; B*heads for attention) */
+  int heads;          /* z -> (z / heads, z % heads); 1 when unused */
+  /* A operand: 4-D tensor [d3][d2][d1][d0] fp16, d0 contiguous (= K direction) */
+  const void* A;
+  int a_dim[4];           /* d0..d3 extents in elements */
+  long long a_stride[3];  /* byte strides of d1..d3 */
+  int a_box[4];           /* TMA box d0..d3; a_box[0] = 64, product of the rest = 128 */
+  /* conv mode (ntaps > 1 or explicit taps): K = ntaps * Ck; tap t reads channels
+     [tap_c[t], tap_c[t] + Ck) at pixel offset (tap_dx[t], tap_dy[t]); OOB reads are zero */
+  int ntaps, Ck;
+  int tap_dx[9], tap_dy[9], tap_c[9];
+  int rows_per_image;     /* conv: H*W of the output (rows m -> image m / rows_per_image) */
+  int img_w, img_h;       /* conv: output width / height */
+  /* batched (attention) addressing of A: coordinate d0 += (z % heads) * a_head_k,
+     d2 = a_zflat ? z : z / heads */
+  int a_head_k, a_zflat;
+  /* B operand: 3-D tensor [d2][d1][d0] fp16 (d0 = K direction, d1 = N direction) */
+  const void* B;
+  int b_dim[3];
+  long long b_stride[2];
+  int b_head_k, b_head_n; /* d0 += (z % heads) * b_head_k; d1 += (z % heads) * b_head_n */
+  /* output */
+  void* C;
+  long long ldc;          /* row stride in elements */
+  long long c_batch_stride, c_head_stride; /* elements; offset = (z/heads)*bs + (z%heads)*hs */
+  /* epilogue */
+  const void* bias;       /* fp16 [N] or NULL */
+  const void* row_bias;   /* fp16 [images, N] or NULL: added per image (time embedding) */
+  const void* residual;   /* fp16, same addressing as C, or NULL */
+  float alpha;            /* y = alpha * acc (+ bias ...) */
+  unsigned flags;
+  int block_n;            /* 16..256, multiple of 16; 0 = choose */
+} GdGemmArgs;
+
+int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
+
+/* GroupNorm over NHWC fp16 (+ optional SiLU). x,y: [N, HW, C]; gamma,beta fp16 [C]. */
+int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int N, int HW,
+                      int C, int groups, float eps, int silu, gd_ustream_t stream);
+/* LayerNorm over the last dim. x,y: [rows, C] fp16. */
+int gd_unet_layernorm(const void* x, void* y, const void* gamma, const void* beta, int rows, int C,
+                      float eps, gd_ustream_t stream);
+/* In-place row softmax of fp16 scores [rows, cols] (row stride ld elements), fp32 math. */
+int gd_unet_softmax(void* s, long long rows, int cols, long long ld, gd_ustream_t stream);
+/* GEGLU: y[r, j] = x[r, j] * gelu_erf(x[r, H + j]); x [rows, 2H], y [rows, H]. */
+int gd_unet_geglu(const void* x, void* y, long long rows, int H, gd_ustream_t stream);
+/* y = a + b (fp16, n elements) */
+int gd_unet_add(const void* a, const void* b, void* y, long long n, gd_ustream_t stream);
+/* nearest-neighbour 2x upsample, NHWC fp16: [N,H,W,C] -> [N,2H,2W,C] */
+int gd_unet_upsample2x(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t stream);
+/* space-to-depth for the stride-2 3x3 convolution: [N,H,W,C] -> [N,H/2,W/2,4C],
+   channel block (py*2+px)*C holds x[2y+py, 2x+px] */
+int gd_unet_space_to_depth(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t stream);
+/* channel concat NHWC: y[..., :Ca] = a, y[..., Ca:] = b */
+int gd_unet_concat(const void* a, const void* b, void* y, long long rows, int Ca, int Cb,
+                   gd_ustream_t stream);
+/* Small-M linear on CUDA cores (time embedding path): y[b, n] = act_out(sum_k act_in(x[b,k]) *
+   W[n,k] + bias[n]); x fp16 [Bm,K], W fp16 [N,K], y fp16 [Bm,N]; Bm <= 16. */
+int gd_unet_small_linear(const void* x, const void* W, const void* bias, void* y, int Bm, int K,
+                         int N, int silu_in, int silu_out, gd_ustream_t stream);
+/* Sinusoidal timestep embedding (flip_sin_to_cos, freq_shift 0): t fp32 [Bm] -> y fp16 [Bm, dim]
+   = [cos | sin]; the timestep is first rounded to fp16 like the reference's t.to(fp16). */
+int gd_unet_timestep_embedding(const float* t, void* y, int Bm, int dim, gd_ustream_t stream);
+/* conv_in: 3x3, pad 1, C_in = 4 (NCHW fp16 input [N,4,H,W]) -> NHWC fp16 [N,H,W,Cout].
+   w fp16 [Cout,3,3,4], bias fp16 [Cout]. */
+int gd_unet_conv_in(const void* x_nchw, const void* w, const void* bias, void* y, int N, int H,
+                    int W, int Cout, gd_ustream_t stream);
+/* conv_out: 3x3, pad 1, NHWC fp16 [N,H,W,Cin] -> NCHW fp32 [N,4,H,W]; w fp16 [4,3,3,Cin]. */
+int gd_unet_conv_out(const void* x, const void* w, const void* bias, float* y_nchw, int N, int H,
+                     int W, int Cin, gd_ustream_t stream);
+/* SDS prologue: latents fp32 [B,4,H,W], noise fp32, per-sample sqrt(abar), sqrt(1-abar) ->
+   x_t fp32 [B,4,H,W] and the duplicated fp16 NCHW UNet input [reps*B,4,H,W]. */
+int gd_unet_add_noise(const float* latents, const float* noise, const float* sqrt_ab,
+                      const float* sqrt_1mab, float* latents_noisy, void* unet_in_f16, int B,
+                      int reps, int chw, gd_ustream_t stream);
+/* SDS epilogue (stable_diffusion_guidance.py:248-265): noise_pred = e_text + s*(e_text-e_uncond),
+   grad = w * (noise_pred - noise); eps fp32 [2B,...] ordered (text, uncond). */
+int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float guidance_scale,
+                     float* noise_pred, float* grad, int B, int chw, gd_ustream_t stream);
+
+const char* gd_unet_last_error(void);
+uint64_t gd_unet_launch_count(void);
+const char* gd_unet_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GD_UNET_H_ */

@@ -1,0 +1,143 @@
+"""GPU: every UNet operator of the C ABI (include/gd_unet.h) against a plain PyTorch fp32
+reference of the same op on the same fp16 inputs. Tolerance: 2e-3 relative (fp16 output rounding
+is 4.9e-4; north_star allows 1e-3 rel on the final SDS gradient, checked in test_unet_gpu.py)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def maxrel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from garmentdreamer_b200 import unet_ops
+    unet_ops.lib()
+    return unet_ops
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 16), (256, 320, 320), (1000, 1280, 640), (4096, 320, 2560),
+                                   (77 * 2, 1024, 1280), (64, 1280, 1280), (8192, 2560, 320)])
+def test_linear(ops, M, K, N):
+    x, w, b = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(N)
+    y = ops.linear(x, w, b)
+    ref = x.float() @ w.float().t() + b.float()
+    assert maxrel(y, ref) < 2e-3 and rel(y, ref) < 1e-3
+
+
+def test_linear_epilogues(ops):
+    M, K, N = 512, 640, 640
+    x, w, b, r = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(N), rnd(M, N)
+    ref = x.float() @ w.float().t() + b.float()
+    assert rel(ops.linear(x, w, b, residual=r), ref + r.float()) < 1e-3
+    assert rel(ops.linear(x, w, b, flags=ops.EPI_SILU), F.silu(ref)) < 1e-3
+    assert rel(ops.linear(x, w, None, alpha=0.125), 0.125 * (x.float() @ w.float().t())) < 1e-3
+    # GEGLU: weight rows interleaved in blocks of 16 (value, gate)
+    H = N // 2
+    val, gate = ref[:, :H], ref[:, H:]
+    perm = torch.cat([torch.cat([torch.arange(i, i + 16), torch.arange(H + i, H + i + 16)]) for i in range(0, H, 16)]).cuda()
+    y = ops.linear(x, w[perm].contiguous(), b[perm].contiguous(), flags=ops.EPI_GEGLU)
+    assert y.shape == (M, H)
+    assert rel(y, val * F.gelu(gate)) < 1e-3
+    assert rel(ops.geglu(ref.half()), ref.half().float()[:, :H] * F.gelu(ref.half().float()[:, H:])) < 1e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 320), (3, 16, 16, 1280, 640),
+                                            (2, 8, 8, 1280, 1280), (1, 8, 8, 2560, 1280), (1, 64, 64, 64, 128)])
+def test_conv3x3(ops, N, H, W, Cin, Cout):
+    x = rnd(N, H, W, Cin)
+    w = rnd(Cout, 3, 3, Cin, scale=(9 * Cin) ** -0.5)
+    b, temb, res = rnd(Cout), rnd(N, Cout), rnd(N, H, W, Cout)
+    y = ops.conv3x3(x, w, b, row_bias=temb, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b.float(), padding=1)
+    ref = (ref + temb.float()[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    assert maxrel(y, ref) < 2e-3 and rel(y, ref) < 1e-3
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 64, 64, 320), (2, 32, 32, 640), (2, 16, 16, 1280)])
+def test_conv3x3_stride2(ops, N, H, W, C):
+    x, w, b = rnd(N, H, W, C), rnd(C, 3, 3, C, scale=(9 * C) ** -0.5), rnd(C)
+    y = ops.conv3x3_stride2(x, w, b)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b.float(), stride=2, padding=1)
+    assert rel(y, ref.permute(0, 2, 3, 1)) < 1e-3
+
+
+@pytest.mark.parametrize("B,Tq,Tk,heads", [(2, 4096, 4096, 5), (2, 1024, 1024, 10), (2, 256, 77, 20), (1, 64, 64, 20)])
+def test_attention(ops, B, Tq, Tk, heads):
+    C = heads * 64
+    q, k, xv = rnd(B, Tq, C), rnd(B, Tk, C, seed=1), rnd(B, Tk, C, seed=2)
+    wv = rnd(C, C, scale=C ** -0.5)
+    ldv = (Tk + 7) // 8 * 8
+    vt = ops.linear_transposed(xv, wv, ldv)
+    v_ref = (xv.float() @ wv.float().t())
+    assert rel(vt[:, :, :Tk].transpose(1, 2), v_ref) < 1e-3
+    s = ops.attn_scores(q, k, heads, 0.125)
+    qh = q.float().view(B, Tq, heads, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Tk, heads, 64).permute(0, 2, 1, 3)
+    s_ref = 0.125 * qh @ kh.transpose(-1, -2)
+    assert rel(s[:, :, :Tk].view(B, heads, Tq, Tk), s_ref) < 1e-3
+    ops.softmax_(s, Tk)
+    assert rel(s[:, :, :Tk].view(B, heads, Tq, Tk), s_ref.softmax(-1)) < 2e-3
+    o = torch.empty(B, Tq, C, dtype=torch.float16, device="cuda")
+    ops.attn_values(s, vt, heads, Tk, o)
+    vh = vt[:, :, :Tk].float().view(B, heads, 64, Tk).transpose(-1, -2)
+    o_ref = (s_ref.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B, Tq, C)
+    assert rel(o, o_ref) < 3e-3
+
+
+def test_norms_and_elementwise(ops):
+    x = rnd(2, 32, 32, 640)
+    g, b = rnd(640), rnd(640)
+    ref = F.group_norm(x.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), 1e-5)
+    assert rel(ops.groupnorm(x, g, b, eps=1e-5), ref.permute(0, 2, 3, 1)) < 1e-3
+    assert rel(ops.groupnorm(x, g, b, eps=1e-5, silu=True), F.silu(ref).permute(0, 2, 3, 1)) < 1e-3
+    x320 = rnd(1, 64, 64, 320)
+    g3, b3 = rnd(320), rnd(320)
+    ref = F.group_norm(x320.float().permute(0, 3, 1, 2), 32, g3.float(), b3.float(), 1e-6)
+    assert rel(ops.groupnorm(x320, g3, b3, eps=1e-6), ref.permute(0, 2, 3, 1)) < 1e-3
+    t = rnd(300, 1280)
+    g2, b2 = rnd(1280), rnd(1280)
+    assert rel(ops.layernorm(t, g2, b2), F.layer_norm(t.float(), (1280,), g2.float(), b2.float(), 1e-5)) < 1e-3
+    a, c = rnd(1000, 64), rnd(1000, 64, seed=3)
+    assert torch.equal(ops.add(a, c), a + c)
+    u = rnd(2, 8, 8, 1280)
+    assert torch.equal(ops.upsample2x(u), F.interpolate(u.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1))
+    p, q = rnd(2, 16, 16, 640), rnd(2, 16, 16, 1280)
+    assert torch.equal(ops.concat(p, q), torch.cat([p, q], -1))
+
+
+def test_time_embedding_and_small_ops(ops):
+    t = torch.tensor([20.0, 500.0, 979.0, 980.0], device="cuda")
+    e = ops.timestep_embedding(t, 320)
+    th = t.half().float()
+    freq = torch.exp(-math.log(10000.0) * torch.arange(160, device="cuda").float() / 160)
+    ref = torch.cat([torch.cos(th[:, None] * freq), torch.sin(th[:, None] * freq)], -1)
+    assert (e.float() - ref).abs().max() < 2e-3
+    x, w, b = rnd(8, 1280), rnd(640, 1280, scale=1280 ** -0.5), rnd(640)
+    ref = F.silu(x.float()) @ w.float().t() + b.float()
+    assert rel(ops.small_linear(x, w, b, silu_in=True), ref) < 1e-3
+    assert rel(ops.small_linear(x, w, b, silu_out=True), F.silu(x.float() @ w.float().t() + b.float())) < 1e-3
+    xi = rnd(2, 4, 64, 64)
+    wi, bi = rnd(320, 3, 3, 4, scale=1 / 6), rnd(320)
+    ref = F.conv2d(xi.float(), wi.float().permute(0, 3, 1, 2), bi.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel(ops.conv_in(xi, wi, bi), ref) < 1e-3
+    xo = rnd(2, 64, 64, 320)
+    wo, bo = rnd(4, 3, 3, 320, scale=(9 * 320) ** -0.5), rnd(4)
+    ref = F.conv2d(xo.float().permute(0, 3, 1, 2), wo.float().permute(0, 3, 1, 2), bo.float(), padding=1)
+    assert rel(ops.conv_out(xo, wo, bo), ref) < 1e-3
