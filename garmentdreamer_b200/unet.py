@@ -1,0 +1,184 @@
+"""B200-native SD-2.1-base UNet forward (fp16, channels-last) behind the interface the reference
+guidance expects from ``pipe.unet`` (stable_diffusion_guidance.py:96-97,146-157):
+
+    unet(latents_fp16, t_fp16, encoder_hidden_states=emb_fp16).sample
+
+Python only orders the operator calls; every kernel is in libgd_unet.so (include/gd_unet.h):
+the tcgen05/TMEM/TMA GEMM for all Linear / conv-as-GEMM / QK^T / PV contractions plus small fused
+normalisation / softmax kernels. Weights arrive as a diffusers-layout state dict (key scheme of
+UNet2DConditionModel; the in-tree statement of the module tree is
+Garment_Deformer_NeTF/netf/vsd/lora_unet.py:119-422) and are re-laid-out once for the kernels.
+"""
+from types import SimpleNamespace
+
+import torch
+
+from . import unet_ops as ops
+
+BLOCK_OUT = (320, 640, 1280, 1280)
+HEADS = (5, 10, 20, 20)
+DOWN_ATTN = (True, True, True, False)
+UP_ATTN = (False, True, True, True)
+
+
+def _geglu_perm(hidden):
+    """Row order that puts 16 value rows next to their 16 gate rows (GD_EPI_GEGLU)."""
+    idx = []
+    for i in range(0, hidden, 16):
+        idx += list(range(i, i + 16)) + list(range(hidden + i, hidden + i + 16))
+    return torch.tensor(idx, dtype=torch.long)
+
+
+class UNetB200:
+    def __init__(self, state_dict, device="cuda", use_cuda_graph=True):
+        self.device = torch.device(device)
+        ops.lib()  # fail loudly if the CUDA library is missing
+        self.w = {}
+        for k, v in state_dict.items():
+            self.w[k] = self._convert(k, v)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self.dtype = torch.float16
+        self.training = False
+
+    # ---- module-like surface used by the reference guidance ---------------------------------
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(self.w.values())
+
+    def to(self, *a, **k):
+        return self
+
+    def requires_grad_(self, flag=False):
+        return self
+
+    def _convert(self, key, v):
+        v = v.detach().to(self.device, torch.float16)
+        if v.dim() == 4:
+            if v.shape[2] == 1:  # conv_shortcut 1x1 -> Linear
+                return v.reshape(v.shape[0], v.shape[1]).contiguous()
+            return v.permute(0, 2, 3, 1).contiguous()  # [Cout,3,3,Cin]
+        if key.endswith("ff.net.0.proj.weight") or key.endswith("ff.net.0.proj.bias"):
+            return v[_geglu_perm(v.shape[0] // 2).to(v.device)].contiguous()
+        return v.contiguous()
+
+    # ---- blocks --------------------------------------------------------------------------------
+    def _resnet(self, p, x, emb):
+        w = self.w
+        N, H, W, Cin = x.shape
+        temb = ops.small_linear(emb, w[p + ".time_emb_proj.weight"], w[p + ".time_emb_proj.bias"], silu_in=True)
+        h = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=1e-5, silu=True)
+        h = ops.conv3x3(h, w[p + ".conv1.weight"], w[p + ".conv1.bias"], row_bias=temb)
+        h = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], eps=1e-5, silu=True, out=h)
+        if p + ".conv_shortcut.weight" in w:
+            x = ops.linear(x.view(N * H * W, Cin), w[p + ".conv_shortcut.weight"], w[p + ".conv_shortcut.bias"])
+            x = x.view(N, H, W, -1)
+        return ops.conv3x3(h, w[p + ".conv2.weight"], w[p + ".conv2.bias"], residual=x)
+
+    def _attention(self, p, xn, ctx, heads, resid):
+        """xn [B,T,C] normalised tokens, ctx [B,Tk,Ck] (== xn for self-attention)."""
+        w = self.w
+        B, T, C = xn.shape
+        Tk = ctx.shape[1]
+        q = ops.linear(xn, w[p + ".to_q.weight"])
+        k = ops.linear(ctx, w[p + ".to_k.weight"])
+        vt = ops.linear_transposed(ctx, w[p + ".to_v.weight"], (Tk + 7) // 8 * 8)
+        s = ops.attn_scores(q, k, heads, 0.125)
+        ops.softmax_(s, Tk)
+        o = torch.empty((B, T, C), dtype=torch.float16, device=xn.device)
+        ops.attn_values(s, vt, heads, Tk, o)
+        return ops.linear(o, w[p + ".to_out.0.weight"], w[p + ".to_out.0.bias"], residual=resid)
+
+    def _transformer(self, p, x, ctx, heads):
+        w = self.w
+        N, H, W, C = x.shape
+        h = ops.groupnorm(x, w[p + ".norm.weight"], w[p + ".norm.bias"], eps=1e-6, silu=False)
+        h = ops.linear(h.view(N, H * W, C), w[p + ".proj_in.weight"], w[p + ".proj_in.bias"])
+        b = p + ".transformer_blocks.0"
+        n1 = ops.layernorm(h, w[b + ".norm1.weight"], w[b + ".norm1.bias"])
+        h = self._attention(b + ".attn1", n1, n1, heads, h)
+        n2 = ops.layernorm(h, w[b + ".norm2.weight"], w[b + ".norm2.bias"])
+        h = self._attention(b + ".attn2", n2, ctx, heads, h)
+        n3 = ops.layernorm(h, w[b + ".norm3.weight"], w[b + ".norm3.bias"])
+        f = ops.linear(n3, w[b + ".ff.net.0.proj.weight"], w[b + ".ff.net.0.proj.bias"], flags=ops.EPI_GEGLU)
+        h = ops.linear(f, w[b + ".ff.net.2.weight"], w[b + ".ff.net.2.bias"], residual=h)
+        out = ops.linear(h, w[p + ".proj_out.weight"], w[p + ".proj_out.bias"], residual=x.view(N, H * W, C))
+        return out.view(N, H, W, C)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def _forward_impl(self, sample, t_f32, ctx):
+        w = self.w
+        x = ops.conv_in(sample, w["conv_in.weight"], w["conv_in.bias"])
+        temb = ops.timestep_embedding(t_f32, 320)
+        emb = ops.small_linear(temb, w["time_embedding.linear_1.weight"], w["time_embedding.linear_1.bias"], silu_out=True)
+        emb = ops.small_linear(emb, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"])
+        skips = [x]
+        for i in range(4):
+            for j in range(2):
+                x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, emb)
+                if DOWN_ATTN[i]:
+                    x = self._transformer(f"down_blocks.{i}.attentions.{j}", x, ctx, HEADS[i])
+                skips.append(x)
+            if i < 3:
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                x = ops.conv3x3_stride2(x, w[p + ".weight"], w[p + ".bias"])
+                skips.append(x)
+        x = self._resnet("mid_block.resnets.0", x, emb)
+        x = self._transformer("mid_block.attentions.0", x, ctx, 20)
+        x = self._resnet("mid_block.resnets.1", x, emb)
+        rev_heads = HEADS[::-1]
+        for i in range(4):
+            for j in range(3):
+                x = ops.concat(x, skips.pop())
+                x = self._resnet(f"up_blocks.{i}.resnets.{j}", x, emb)
+                if UP_ATTN[i]:
+                    x = self._transformer(f"up_blocks.{i}.attentions.{j}", x, ctx, rev_heads[i])
+            if i < 3:
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                x = ops.conv3x3(ops.upsample2x(x), w[p + ".weight"], w[p + ".bias"])
+        x = ops.groupnorm(x, w["conv_norm_out.weight"], w["conv_norm_out.bias"], eps=1e-5, silu=True)
+        return ops.conv_out(x, w["conv_out.weight"], w["conv_out.bias"])  # NCHW fp32 (fp16-rounded)
+
+    def forward_f32(self, sample, timestep, encoder_hidden_states):
+        """sample [B,4,H,W] (any float dtype, NCHW), timestep [B], ctx [B,77,1024] -> fp32 NCHW."""
+        if not sample.is_cuda:
+            raise RuntimeError("garmentdreamer_b200 UNet is CUDA-only (no CPU fallback)")
+        sample = sample.to(torch.float16).contiguous()
+        t_f32 = timestep.to(torch.float32).reshape(-1).contiguous()
+        if t_f32.numel() == 1 and sample.shape[0] > 1:
+            t_f32 = t_f32.expand(sample.shape[0]).contiguous()
+        ctx = encoder_hidden_states.to(torch.float16).contiguous()
+        if not self.use_cuda_graph:
+            return self._forward_impl(sample, t_f32, ctx)
+        key = (tuple(sample.shape), tuple(ctx.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            g = SimpleNamespace(sample=sample.clone(), t=t_f32.clone(), ctx=ctx.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture (lazy init, allocator)
+                self._forward_impl(g.sample, g.t, g.ctx)
+            torch.cuda.current_stream().wait_stream(side)
+            g.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g.graph):
+                g.out = self._forward_impl(g.sample, g.t, g.ctx)
+            self._graphs[key] = g
+        g.sample.copy_(sample); g.t.copy_(t_f32); g.ctx.copy_(ctx)
+        g.graph.replay()
+        return g.out
+
+    def __call__(self, sample, timestep, encoder_hidden_states=None, **kwargs):
+        out = self.forward_f32(sample, timestep, encoder_hidden_states)
+        return SimpleNamespace(sample=out.to(sample.dtype))
+
+
+def smoke():
+    """Tiny invocation of the tcgen05 GEMM against torch (called by __graft_entry__.smoke())."""
+    x = torch.randn(256, 320, device="cuda").half()
+    wt = (torch.randn(640, 320, device="cuda") * 320 ** -0.5).half()
+    y = ops.linear(x, wt)
+    ref = x.float() @ wt.float().t()
+    err = float((y.float() - ref).norm() / ref.norm())
+    assert err < 1e-3, f"tcgen05 GEMM differs from torch by rel {err}"
