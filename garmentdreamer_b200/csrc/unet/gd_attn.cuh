@@ -1,0 +1,241 @@
+// Fused attention for sm_100a: O = softmax(scale * Q K^T) V per (batch, head), head_dim 64.
+//
+// One CTA per 128 query rows of one (batch, head); 192 threads, warp-specialised:
+//   warp 0    : TMA producer (Q once; K tiles twice; V^T tiles once)
+//   warp 1    : tcgen05.mma issuer  S = Q K_j^T  (M128 N128 K64, TMEM, double buffered)
+//                                   O += P_j V_j (M128 N64  K128, TMEM)
+//   warps 2-5 : softmax: tcgen05.ld S, P = exp2((S - m) * c) -> fp16 -> shared memory in the
+//               128B-swizzled K-major layout the MMA reads as its A operand
+// Two passes over the keys: pass 1 only reduces the row maxima m (no exp), pass 2 recomputes S and
+// accumulates O and the row sums with the FINAL maximum, so O never needs rescaling in TMEM.
+// The S matrix (1.3 GB per 64x64 layer at batch 8) never touches HBM.
+#pragma once
+#include "gd_gemm.cuh"
+
+namespace gdu {
+
+struct AttnParams {
+  int Tq, Tk, heads;
+  int n_kv;              // ceil(Tk / 128)
+  float scale_log2e;     // softmax scale * log2(e)
+  __half* O;             // [B, Tq, ldo]
+  long long ldo;
+};
+
+constexpr int kAttnThreads = 192;
+constexpr uint32_t kQBytes = 128 * 64 * 2, kKBytes = 128 * 64 * 2, kVBytes = 2 * 64 * 64 * 2, kPBytes = 2 * 128 * 64 * 2;
+
+__device__ __forceinline__ void bar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(b)) : "memory");
+}
+__device__ __forceinline__ uint32_t umma_idesc_f16_n(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kQBytes;          // 2 stages
+  uint8_t* sV = sK + 2 * kKBytes;      // 2 stages x 2 key blocks x [64 d x 64 keys]
+  uint8_t* sP = sV + 2 * kVBytes;      // 2 buffers x 2 key blocks x [128 rows x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;   uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;   uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;   uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 13;  uint64_t* p_empty = bars + 15;
+  uint64_t* o_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
+  const int n = p.n_kv, iters = 2 * n;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    bar_init(q_full, 1);
+    for (int s = 0; s < 2; s++) {
+      bar_init(&k_full[s], 1); bar_init(&k_empty[s], 1);
+      bar_init(&v_full[s], 1); bar_init(&v_empty[s], 1);
+      bar_init(&s_full[s], 1); bar_init(&s_empty[s], 4);   // one arrive per softmax warp
+      bar_init(&p_full[s], 4); bar_init(&p_empty[s], 1);
+    }
+    bar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S0 = tmem, tmem_O = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      bar_expect_tx(q_full, kQBytes);
+      tma_load_3d(sQ, &tmQ, q_full, h * 64, m_blk * 128, b);
+      for (int i = 0; i < iters; i++) {
+        const int j = i % n, s = i & 1;
+        bar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
+        bar_expect_tx(&k_full[s], kKBytes);
+        tma_load_3d(sK + s * kKBytes, &tmK, &k_full[s], h * 64, j * 128, b);
+        if (i >= n) {
+          const int vi = i - n, vs = vi & 1;
+          bar_wait(&v_empty[vs], ((vi >> 1) & 1) ^ 1);
+          bar_expect_tx(&v_full[vs], kVBytes);
+          tma_load_3d(sV + vs * kVBytes, &tmV, &v_full[vs], j * 128, h * 64, b);
+          tma_load_3d(sV + vs * kVBytes + 64 * 64 * 2, &tmV, &v_full[vs], j * 128 + 64, h * 64, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = umma_idesc_f16_n(128), idesc_o = umma_idesc_f16_n(64);
+    bar_wait(q_full, 0);
+    auto issue_S = [&](int i) {
+      const int s = i & 1;
+      bar_wait(&k_full[s], (i >> 1) & 1);
+      bar_wait(&s_empty[s], ((i >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint64_t da = umma_desc_sw128(s2u(sQ)), db = umma_desc_sw128(s2u(sK + s * kKBytes));
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_f16(tmem_S0 + s * 128, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    issue_S(0);
+    for (int i = 0; i < iters; i++) {
+      if (i + 1 < iters) issue_S(i + 1);
+      if (i >= n) {
+        const int vi = i - n, vs = vi & 1;   // P / V buffers are indexed from the start of pass 2
+        bar_wait(&p_full[vs], (vi >> 1) & 1);
+        bar_wait(&v_full[vs], (vi >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+#pragma unroll
+          for (int kb = 0; kb < 2; kb++) {
+            const uint64_t da = umma_desc_sw128(s2u(sP + vs * kPBytes + kb * 128 * 64 * 2));
+            const uint64_t db = umma_desc_sw128(s2u(sV + vs * kVBytes + kb * 64 * 64 * 2));
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma_f16(tmem_O, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_o, (vi | kb | k) ? 1u : 0u);
+          }
+          umma_commit(&p_empty[vs]);
+          umma_commit(&v_empty[vs]);
+          if (i == iters - 1) umma_commit(o_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;                  // row inside the 128-row tile
+    const int row = m_blk * 128 + r;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    for (int i = 0; i < iters; i++) {
+      const int j = i % n, s = i & 1;
+      const int kmax = p.Tk - j * 128;            // keys >= kmax in this tile are padding
+      bar_wait(&s_full[s], (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (i < n) {
+        // ---- pass 1: row maximum ----
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S0 + s * 128 + lane_base + c * 32, v);
+#pragma unroll
+          for (int t = 0; t < 32; t++)
+            if (c * 32 + t < kmax) m = fmaxf(m, __uint_as_float(v[t]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(&s_empty[s]);
+      } else {
+        // ---- pass 2: P = exp2((S - m) * c), row sums, P -> shared memory (A operand of P V) ----
+        const int vi = i - n, ps = vi & 1;
+        bar_wait(&p_empty[ps], ((vi >> 1) & 1) ^ 1);
+        const float mc = m * p.scale_log2e;
+        uint8_t* prow = sP + ps * kPBytes + r * 128;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S0 + s * 128 + lane_base + c * 32, v);
+          if (c == 3) {  // all TMEM reads of this S buffer are done
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(&s_empty[s]);
+          }
+          uint8_t* blk = prow + (c >> 1) * (128 * 64 * 2);   // key block 0/1 of the tile
+#pragma unroll
+          for (int g = 0; g < 4; g++) {                       // 4 chunks of 8 keys = 16 bytes
+            __align__(16) __half2 hv[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              const int k0 = c * 32 + g * 8 + 2 * t;
+              float e0 = exp2f(__uint_as_float(v[g * 8 + 2 * t]) * p.scale_log2e - mc);
+              float e1 = exp2f(__uint_as_float(v[g * 8 + 2 * t + 1]) * p.scale_log2e - mc);
+              if (k0 >= kmax) e0 = 0.f;
+              if (k0 + 1 >= kmax) e1 = 0.f;
+              hv[t] = __floats2half2_rn(e0, e1);
+              const float2 back = __half22float2(hv[t]);    // sum what the MMA will actually see
+              l += back.x + back.y;
+            }
+            const int chunk = (c & 1) * 4 + g;               // 16-byte chunk index in the 128 B row
+            *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(hv);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
+        __syncwarp();
+        if (lane == 0) bar_arrive(&p_full[ps]);
+      }
+    }
+    // ---- epilogue: O / l ----
+    bar_wait(o_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float inv = 1.0f / l;
+    __half* dst = p.O + ((long long)b * p.Tq + row) * p.ldo + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      uint32_t v[32];
+      tmem_ld32(tmem_O + lane_base + c * 32, v);
+      if (row < p.Tq) {
+        __align__(16) __half o[32];
+#pragma unroll
+        for (int t = 0; t < 32; t++) o[t] = __float2half_rn(__uint_as_float(v[t]) * inv);
+#pragma unroll
+        for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst + c * 32)[u] = reinterpret_cast<const uint4*>(o)[u];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace gdu

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "gd_gemm.cuh"
+#include "gd_attn.cuh"
 
 namespace {
 thread_local char g_err[512] = {0};
@@ -62,18 +63,19 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 
 namespace gdu {
 
-// ---- GroupNorm (+SiLU), NHWC fp16: one CTA per (image, group) -----------------------------
+// ---- GroupNorm (+SiLU), NHWC fp16 -------------------------------------------------------------
+// Pass 1: grid (image*group, splits): partial sum / sum-of-squares over a slice of the pixels,
+// written to part[(n*groups+g)*splits + s] (fixed-order merge in pass 2 => deterministic).
 __global__ void __launch_bounds__(256)
-k_groupnorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
-            const __half* __restrict__ beta, int HW, int C, int groups, float eps, int do_silu) {
-  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+k_gn_stats(const __half* __restrict__ x, float2* __restrict__ part, int HW, int C, int groups, int splits) {
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups, sp = blockIdx.y;
   const int cpg = C / groups, cp2 = cpg >> 1;  // cpg is even for every SD layer
+  const int p0 = (int)((long long)HW * sp / splits), p1 = (int)((long long)HW * (sp + 1) / splits);
   const __half2* xb = reinterpret_cast<const __half2*>(x + (size_t)n * HW * C + (size_t)g * cpg);
-  __half2* yb = reinterpret_cast<__half2*>(y + (size_t)n * HW * C + (size_t)g * cpg);
-  const int total = HW * cp2;
+  const int total = (p1 - p0) * cp2;
   float s = 0.f, ss = 0.f;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int pix = i / cp2, c = i % cp2;
+    const int pix = p0 + i / cp2, c = i % cp2;
     const float2 v = __half22float2(xb[(size_t)pix * (C >> 1) + c]);
     s += v.x + v.y;
     ss += v.x * v.x + v.y * v.y;
@@ -83,22 +85,52 @@ k_groupnorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* 
   for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
   if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
   __syncthreads();
-  s = 0.f; ss = 0.f;
+  if (threadIdx.x == 0) {
+    s = 0.f; ss = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; w++) { s += sh[0][w]; ss += sh[1][w]; }
-  const float inv_n = 1.0f / (float)(HW * cpg);
-  const float mean = s * inv_n;
-  const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
-  const float rstd = rsqrtf(var + eps);
-  const __half2* g2 = reinterpret_cast<const __half2*>(gamma + (size_t)g * cpg);
-  const __half2* b2 = reinterpret_cast<const __half2*>(beta + (size_t)g * cpg);
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int pix = i / cp2, c = i % cp2;
-    const float2 v = __half22float2(xb[(size_t)pix * (C >> 1) + c]);
-    const float2 ga = __half22float2(g2[c]), be = __half22float2(b2[c]);
-    float a = (v.x - mean) * rstd * ga.x + be.x, b = (v.y - mean) * rstd * ga.y + be.y;
-    if (do_silu) { a = silu(a); b = silu(b); }
-    yb[(size_t)pix * (C >> 1) + c] = __floats2half2_rn(a, b);
+    for (int w = 0; w < 8; w++) { s += sh[0][w]; ss += sh[1][w]; }
+    part[(size_t)blockIdx.x * splits + sp] = make_float2(s, ss);
+  }
+}
+// Pass 2: grid (image, pixel chunks): per-channel scale/shift table in shared memory, then a
+// vectorised y = x*a + b (+SiLU) sweep over the chunk (8 channels per 16-byte access).
+__global__ void __launch_bounds__(256)
+k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y, const float2* __restrict__ part,
+           const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int groups, int splits,
+           float eps, int do_silu, int pix_per_cta) {
+  extern __shared__ float2 s_ab[];  // [C] (scale, shift)
+  const int n = blockIdx.x, cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float s = 0.f, ss = 0.f;
+    for (int k = 0; k < splits; k++) {
+      const float2 p = part[((size_t)n * groups + g) * splits + k];
+      s += p.x; ss += p.y;
+    }
+    const float inv_n = 1.0f / (float)(HW * cpg);
+    const float mean = s * inv_n;
+    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + eps);
+    const float a = rstd * __half2float(gamma[c]);
+    s_ab[c] = make_float2(a, __half2float(beta[c]) - mean * a);
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C);
+  uint4* yb = reinterpret_cast<uint4*>(y + (size_t)n * HW * C);
+  for (int i = p0 * C8 + threadIdx.x; i < p1 * C8; i += blockDim.x) {
+    const int c0 = (i % C8) << 3;
+    uint4 v = xb[i];
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 f = __half22float2(h[k]);
+      const float2 ab0 = s_ab[c0 + 2 * k], ab1 = s_ab[c0 + 2 * k + 1];
+      float a = f.x * ab0.x + ab0.y, b = f.y * ab1.x + ab1.y;
+      if (do_silu) { a = silu(a); b = silu(b); }
+      h[k] = __floats2half2_rn(a, b);
+    }
+    yb[i] = v;
   }
 }
 
@@ -235,42 +267,45 @@ __global__ void k_timestep_embedding(const float* __restrict__ t, __half* __rest
   y[(size_t)b * dim + k] = __float2half_rn(cosf(a));         // flip_sin_to_cos: [cos | sin]
   y[(size_t)b * dim + half + k] = __float2half_rn(sinf(a));
 }
-// conv_in: Cin = 4, NCHW fp16 in -> NHWC fp16 out. One thread per (pixel, 8 output channels).
-__global__ void __launch_bounds__(256)
+// conv_in: Cin = 4, NCHW fp16 in -> NHWC fp16 out. Weights staged in shared memory; one thread
+// per pixel keeps its 3x3x4 input patch in registers and walks the output channels.
+__global__ void __launch_bounds__(128)
 k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
           __half* __restrict__ y, int N, int H, int W, int Cout) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int C8 = Cout >> 3;
-  if (i >= (long long)N * H * W * C8) return;
-  const int cg = (int)(i % C8);
-  long long p = i / C8;
-  const int px = (int)(p % W); p /= W;
-  const int py = (int)(p % H);
-  const int n = (int)(p / H);
-  float acc[8];
+  extern __shared__ __half s_w[];  // [Cout][36] + [Cout] bias
+  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[Cout * 36 + i] = bias[i];
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  float in[36];
 #pragma unroll
-  for (int j = 0; j < 8; j++) acc[j] = __half2float(bias[cg * 8 + j]);
-  for (int ky = 0; ky < 3; ky++) {
-    const int iy = py + ky - 1;
-    if (iy < 0 || iy >= H) continue;
+  for (int ky = 0; ky < 3; ky++)
+#pragma unroll
     for (int kx = 0; kx < 3; kx++) {
-      const int ix = px + kx - 1;
-      if (ix < 0 || ix >= W) continue;
-      float in[4];
+      const int iy = py + ky - 1, ix = px + kx - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
 #pragma unroll
-      for (int c = 0; c < 4; c++) in[c] = __half2float(x[(((size_t)n * 4 + c) * H + iy) * W + ix]);
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const __half* wp = w + (((size_t)(cg * 8 + j) * 3 + ky) * 3 + kx) * 4;
-#pragma unroll
-        for (int c = 0; c < 4; c++) acc[j] += in[c] * __half2float(wp[c]);
-      }
+      for (int c = 0; c < 4; c++)
+        in[(ky * 3 + kx) * 4 + c] = ok ? __half2float(x[(((size_t)n * 4 + c) * H + iy) * W + ix]) : 0.f;
     }
-  }
-  __align__(16) __half o[8];
+  __half* yp = y + (size_t)pix * Cout;
+  for (int co = 0; co < Cout; co += 8) {
+    __align__(16) __half o[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) o[j] = __float2half_rn(acc[j]);
-  *reinterpret_cast<uint4*>(y + (((size_t)n * H + py) * W + px) * Cout + cg * 8) = *reinterpret_cast<const uint4*>(o);
+    for (int j = 0; j < 8; j++) {
+      const __half2* wp = reinterpret_cast<const __half2*>(s_w + (co + j) * 36);
+      float acc = __half2float(s_w[Cout * 36 + co + j]);
+#pragma unroll
+      for (int k = 0; k < 18; k++) {
+        const float2 ww = __half22float2(wp[k]);
+        acc += in[2 * k] * ww.x + in[2 * k + 1] * ww.y;
+      }
+      o[j] = __float2half_rn(acc);
+    }
+    *reinterpret_cast<uint4*>(yp + co) = *reinterpret_cast<const uint4*>(o);
+  }
 }
 // conv_out: Cout = 4, NHWC fp16 in -> NCHW fp32 out. One warp per pixel.
 __global__ void __launch_bounds__(256)
@@ -398,8 +433,10 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
-  int stages = (int)((200 * 1024) / stage_bytes);
-  if (stages > 8) stages = 8;
+  // <= ~110 KB per CTA so that two CTAs share an SM: one's epilogue overlaps the other's main loop
+  int stages = (int)((108 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
   if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
   p.stages = stages;
   const size_t smem = stages * stage_bytes + 1024 + 256;
@@ -415,12 +452,61 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   return GD_UNET_OK;
 }
 
+int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq, int Tk,
+                       long long ldq, long long ldk, long long ldv, long long ldo, float scale, gd_ustream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !k || !vt || !out || B < 1 || heads < 1 || Tq < 1 || Tk < 1) return fail(GD_UNET_ERR_INVALID_ARG, "flash_attn: bad argument");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return fail(GD_UNET_ERR_INVALID_ARG, "flash_attn: leading dims must be multiples of 8");
+  const int C = heads * 64;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    cuuint64_t d[3] = {(cuuint64_t)C, (cuuint64_t)Tq, (cuuint64_t)B};
+    cuuint64_t st[2] = {(cuuint64_t)ldq * 2, (cuuint64_t)Tq * ldq * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    int rc = make_map(&tmQ, q, 3, d, st, box);
+    if (rc != GD_UNET_OK) return rc;
+    cuuint64_t dk[3] = {(cuuint64_t)C, (cuuint64_t)Tk, (cuuint64_t)B};
+    cuuint64_t sk[2] = {(cuuint64_t)ldk * 2, (cuuint64_t)Tk * ldk * 2};
+    rc = make_map(&tmK, k, 3, dk, sk, box);
+    if (rc != GD_UNET_OK) return rc;
+    cuuint64_t dv[3] = {(cuuint64_t)Tk, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t sv[2] = {(cuuint64_t)ldv * 2, (cuuint64_t)C * ldv * 2};
+    cuuint32_t boxv[3] = {64, 64, 1};
+    rc = make_map(&tmV, vt, 3, dv, sv, boxv);
+    if (rc != GD_UNET_OK) return rc;
+  }
+  gdu::AttnParams p;
+  p.Tq = Tq; p.Tk = Tk; p.heads = heads; p.n_kv = (Tk + 127) / 128;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.O = reinterpret_cast<__half*>(out); p.ldo = ldo;
+  const size_t smem = gdu::kQBytes + 2 * gdu::kKBytes + 2 * gdu::kVBytes + 2 * gdu::kPBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gdu::k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail(GD_UNET_ERR_CUDA, "flash_attn: cannot raise dynamic shared memory limit");
+    attr_set = true;
+  }
+  gdu::k_flash_attn<<<dim3((Tq + 127) / 128, B * heads), gdu::kAttnThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  LAUNCH_CHECK("k_flash_attn");
+  return GD_UNET_OK;
+}
+
 int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int N, int HW, int C, int groups,
                       float eps, int silu, gd_ustream_t s) {
-  if (C % groups || (C / groups) % 2) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm: channels per group must be even");
-  gdu::k_groupnorm<<<N * groups, 256, 0, (cudaStream_t)s>>>((const __half*)x, (__half*)y, (const __half*)gamma,
-                                                           (const __half*)beta, HW, C, groups, eps, silu);
-  LAUNCH_CHECK("k_groupnorm");
+  if (C % groups || (C / groups) % 2 || C % 8 || N * groups > 4096)
+    return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm: channels per group must be even, C % 8 == 0");
+  // partial statistics live in a small static device buffer (N*groups*splits float2 <= 512 KB)
+  static float2* part = nullptr;
+  if (!part && cudaMalloc(&part, sizeof(float2) * 4096 * 16) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm: cudaMalloc");
+  const int splits = HW >= 4096 ? 16 : HW >= 1024 ? 8 : HW >= 256 ? 4 : 1;
+  gdu::k_gn_stats<<<dim3(N * groups, splits), 256, 0, (cudaStream_t)s>>>((const __half*)x, part, HW, C, groups, splits);
+  LAUNCH_CHECK("k_gn_stats");
+  int pix_per_cta = (int)((16384 + C - 1) / C);  // ~16k elements per CTA
+  if (pix_per_cta < 1) pix_per_cta = 1;
+  gdu::k_gn_apply<<<dim3(N, (HW + pix_per_cta - 1) / pix_per_cta), 256, sizeof(float2) * C, (cudaStream_t)s>>>(
+      (const __half*)x, (__half*)y, part, (const __half*)gamma, (const __half*)beta, HW, C, groups, splits, eps, silu,
+      pix_per_cta);
+  LAUNCH_CHECK("k_gn_apply");
   return GD_UNET_OK;
 }
 int gd_unet_layernorm(const void* x, void* y, const void* gamma, const void* beta, int rows, int C, float eps, gd_ustream_t s) {
@@ -481,10 +567,10 @@ int gd_unet_timestep_embedding(const float* t, void* y, int Bm, int dim, gd_ustr
   return GD_UNET_OK;
 }
 int gd_unet_conv_in(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int Cout, gd_ustream_t s) {
-  if (Cout % 8) return fail(GD_UNET_ERR_INVALID_ARG, "conv_in: Cout % 8");
-  const long long total = (long long)N * H * W * (Cout / 8);
-  gdu::k_conv_in<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const __half*)x, (const __half*)w,
-                                                                              (const __half*)bias, (__half*)y, N, H, W, Cout);
+  if (Cout % 8 || Cout > 640) return fail(GD_UNET_ERR_INVALID_ARG, "conv_in: Cout % 8, Cout <= 640");
+  const long long pix = (long long)N * H * W;
+  gdu::k_conv_in<<<(unsigned)((pix + 127) / 128), 128, (size_t)Cout * 37 * 2, (cudaStream_t)s>>>(
+      (const __half*)x, (const __half*)w, (const __half*)bias, (__half*)y, N, H, W, Cout);
   LAUNCH_CHECK("k_conv_in");
   return GD_UNET_OK;
 }

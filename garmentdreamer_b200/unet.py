@@ -68,7 +68,7 @@ class UNetB200:
     def _resnet(self, p, x, emb):
         w = self.w
         N, H, W, Cin = x.shape
-        temb = ops.small_linear(emb, w[p + ".time_emb_proj.weight"], w[p + ".time_emb_proj.bias"], silu_in=True)
+        temb = ops.small_linear(emb, w[p + ".time_emb_proj.weight"], w[p + ".time_emb_proj.bias"])  # emb = silu(time emb)
         h = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=1e-5, silu=True)
         h = ops.conv3x3(h, w[p + ".conv1.weight"], w[p + ".conv1.bias"], row_bias=temb)
         h = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], eps=1e-5, silu=True, out=h)
@@ -85,10 +85,7 @@ class UNetB200:
         q = ops.linear(xn, w[p + ".to_q.weight"])
         k = ops.linear(ctx, w[p + ".to_k.weight"])
         vt = ops.linear_transposed(ctx, w[p + ".to_v.weight"], (Tk + 7) // 8 * 8)
-        s = ops.attn_scores(q, k, heads, 0.125)
-        ops.softmax_(s, Tk)
-        o = torch.empty((B, T, C), dtype=torch.float16, device=xn.device)
-        ops.attn_values(s, vt, heads, Tk, o)
+        o = ops.flash_attention(q, k, vt, heads, Tk, 0.125)  # scores never leave TMEM / smem
         return ops.linear(o, w[p + ".to_out.0.weight"], w[p + ".to_out.0.bias"], residual=resid)
 
     def _transformer(self, p, x, ctx, heads):
@@ -113,7 +110,8 @@ class UNetB200:
         x = ops.conv_in(sample, w["conv_in.weight"], w["conv_in.bias"])
         temb = ops.timestep_embedding(t_f32, 320)
         emb = ops.small_linear(temb, w["time_embedding.linear_1.weight"], w["time_embedding.linear_1.bias"], silu_out=True)
-        emb = ops.small_linear(emb, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"])
+        # every consumer (ResnetBlock2D.time_emb_proj) applies SiLU first: do it once here
+        emb = ops.small_linear(emb, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"], silu_out=True)
         skips = [x]
         for i in range(4):
             for j in range(2):

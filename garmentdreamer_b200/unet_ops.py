@@ -50,6 +50,7 @@ def lib():
         L.gd_unet_launch_count.restype = ctypes.c_uint64
         L.gd_unet_gemm.argtypes = [ctypes.POINTER(GdGemmArgs), ctypes.c_void_p]
         vp, i, f, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+        L.gd_unet_flash_attn.argtypes = [vp, vp, vp, vp, i, i, i, i, ll, ll, ll, ll, f, vp]
         L.gd_unet_groupnorm.argtypes = [vp, vp, vp, vp, i, i, i, i, f, i, vp]
         L.gd_unet_layernorm.argtypes = [vp, vp, vp, vp, i, i, f, vp]
         L.gd_unet_softmax.argtypes = [vp, ll, i, ll, vp]
@@ -64,7 +65,7 @@ def lib():
         L.gd_unet_conv_out.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
         L.gd_unet_add_noise.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
         L.gd_unet_sds_grad.argtypes = [vp, vp, vp, f, vp, vp, i, i, vp]
-        for name in ("gemm", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
+        for name in ("gemm", "flash_attn", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
                      "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad"):
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
         _unet = L
@@ -245,6 +246,17 @@ def attn_values(p, vt, heads, Tk, out):
     a.alpha = 1.0
     a.block_n = 64
     _gemm(a)
+    return out
+
+
+def flash_attention(q, k, vt, heads, Tk, scale=0.125, out=None):
+    """Fused softmax(scale q k^T) v; q [B,Tq,C], k [B,Tk,C] (last dim may be a wider row: strides are
+    taken from the tensors), vt = V^T [B,C,ldv]; returns [B,Tq,C]."""
+    B, Tq, C = q.shape[0], q.shape[1], heads * 64
+    if out is None:
+        out = torch.empty((B, Tq, C), dtype=torch.float16, device=q.device)
+    _chk(lib().gd_unet_flash_attn(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Tq, Tk,
+                                  q.stride(1), k.stride(1), vt.stride(1), out.stride(1), scale, _stream()), "flash_attn")
     return out
 
 

@@ -72,6 +72,14 @@ typedef struct {
 
 int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
 
+/* Fused attention, head_dim 64: out[b, :, h*64:(h+1)*64] = softmax(scale * Q_h K_h^T) V_h.
+   q [B,Tq,ldq], k [B,Tk,ldk] (head h in columns h*64..), vt = V^T [B, heads*64, ldv] (keys
+   contiguous), out [B,Tq,ldo]; leading dimensions in elements, multiples of 8. The score matrix
+   stays in TMEM / shared memory. */
+int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq,
+                       int Tk, long long ldq, long long ldk, long long ldv, long long ldo, float scale,
+                       gd_ustream_t stream);
+
 /* GroupNorm over NHWC fp16 (+ optional SiLU). x,y: [N, HW, C]; gamma,beta fp16 [C]. */
 int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int N, int HW,
                       int C, int groups, float eps, int silu, gd_ustream_t stream);

@@ -78,7 +78,7 @@ def test_conv3x3_stride2(ops, N, H, W, C):
     assert rel(y, ref.permute(0, 2, 3, 1)) < 1e-3
 
 
-@pytest.mark.parametrize("B,Tq,Tk,heads", [(2, 4096, 4096, 5), (2, 1024, 1024, 10), (2, 256, 77, 20), (1, 64, 64, 20)])
+@pytest.mark.parametrize("B,Tq,Tk,heads", [(2, 4096, 4096, 5), (2, 1024, 1024, 10), (2, 256, 77, 20), (1, 64, 64, 20), (3, 256, 256, 20), (2, 4096, 77, 5), (1, 1024, 200, 10)])
 def test_attention(ops, B, Tq, Tk, heads):
     C = heads * 64
     q, k, xv = rnd(B, Tq, C), rnd(B, Tk, C, seed=1), rnd(B, Tk, C, seed=2)
@@ -99,6 +99,9 @@ def test_attention(ops, B, Tq, Tk, heads):
     vh = vt[:, :, :Tk].float().view(B, heads, 64, Tk).transpose(-1, -2)
     o_ref = (s_ref.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B, Tq, C)
     assert rel(o, o_ref) < 3e-3
+    # fused kernel (the one the UNet uses): same result without materialising the scores
+    of = ops.flash_attention(q, k, vt, heads, Tk, 0.125)
+    assert rel(of, o_ref) < 3e-3 and maxrel(of, o_ref) < 1e-2
 
 
 def test_norms_and_elementwise(ops):
