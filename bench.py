@@ -175,7 +175,7 @@ def main():
         run_reference(a, rank, world)
         return
     import torch.distributed as dist
-    from garmentdreamer_b200 import _lib, raster
+    from garmentdreamer_b200 import _lib, parallel, raster
     from garmentdreamer_b200.synthetic import garment, sample_cameras
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -196,7 +196,8 @@ def main():
     # xyz 3P | f_dc 3P | opacity P | scales 3P | rotation 4P  (contiguous slices, one H2D copy)
     packed_host = torch.cat([host["xyz"].reshape(-1), host["shs"].reshape(-1), host["opacity"].reshape(-1),
                              host["scales"].reshape(-1), host["rotations"].reshape(-1)]).contiguous().pin_memory()
-    cams = sample_cameras(B * world, S, S)[rank * B:(rank + 1) * B]
+    lo, hi = parallel.shard_views(B * world, rank, world)
+    cams = sample_cameras(B * world, S, S)[lo:hi]
     cam_host = torch.stack([torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos])
                             for c in cams]).contiguous().pin_memory()  # [B,35]
     bg = torch.ones(3, device=dev)
@@ -236,8 +237,7 @@ def main():
         if time_bwd:
             e1.record()
             timers["ev"].append((e0, e1))
-        if world > 1:
-            dist.all_reduce(out)
+        parallel.allreduce_gradients(out)  # the only data-path collective (NCCL over NVLink)
         return out, st
 
     packed_dev = packed_host.to(dev, non_blocking=True)
@@ -258,6 +258,8 @@ def main():
     sampler.start()
     barrier()
     launches0 = lib.gd_launch_count()
+    if guidance is not None:
+        guidance.reset_counters()
     timers["ev"] = []
     step_ms = []
     for _ in range(a.steps):
@@ -273,6 +275,7 @@ def main():
         launches += guidance.launch_count_delta()
     dev_ms = sum(x.elapsed_time(y) for x, y in step_ms)
     bwd_ms = float(np.mean([x.elapsed_time(y) for x, y in timers["ev"]]))
+    sds_roofline = guidance.roofline(*measured_peaks()) if guidance is not None else None
     # ---- end to end through the public API with host buffers (`e2e`) ----
     barrier()
     t_e2e = []
@@ -307,8 +310,9 @@ def main():
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": peak_kind, "algorithmic_bytes": abytes,
                 "launch_ms": bwd_ms, "R": R_total}
-    if guidance is not None:
-        roofline = guidance.roofline(peaks, peak_kind, raster_bwd=roofline)
+    if sds_roofline is not None:
+        sds_roofline["raster_bwd"] = roofline
+        roofline = sds_roofline
     line = {
         "metric": "SDS iterations/sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(3, a.warmup), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,

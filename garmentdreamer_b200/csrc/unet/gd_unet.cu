@@ -222,23 +222,43 @@ __global__ void k_concat(const uint4* __restrict__ a, const uint4* __restrict__ 
   y[i] = c < Ca8 ? a[r * Ca8 + c] : b[r * Cb8 + (c - Ca8)];
 }
 // y[b,n] = act_out(bias[n] + sum_k act_in(x[b,k]) W[n,k]); one warp per output column n.
+// The activations (Bm x K fp16, <= 40 KB) are staged in shared memory once per CTA; every lane
+// then issues all of its 16-byte weight loads before using them (the kernel is DRAM-latency bound).
+template <int KV>  // KV = 16-byte weight vectors per lane (K = KV * 256)
 __global__ void __launch_bounds__(256)
 k_small_linear(const __half* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ bias,
                __half* __restrict__ y, int Bm, int K, int N, int silu_in, int silu_out) {
+  extern __shared__ __half s_x[];  // [Bm][K]
+  for (int i = threadIdx.x; i < Bm * K; i += blockDim.x) {
+    float v = __half2float(x[i]);
+    if (silu_in) v = silu(v);
+    s_x[i] = __float2half_rn(v);
+  }
+  __syncthreads();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= N) return;
+  uint4 wv[KV];
+  const uint4* w4 = reinterpret_cast<const uint4*>(W + (size_t)n * K);
+#pragma unroll
+  for (int j = 0; j < KV; j++) wv[j] = (j * 32 + lane) * 8 < K ? w4[j * 32 + lane] : make_uint4(0, 0, 0, 0);
   float acc[16];
 #pragma unroll
   for (int b = 0; b < 16; b++) acc[b] = 0.f;
-  const __half2* w2 = reinterpret_cast<const __half2*>(W + (size_t)n * K);
-  for (int k = lane; k < (K >> 1); k += 32) {
-    const float2 w = __half22float2(w2[k]);
+#pragma unroll
+  for (int j = 0; j < KV; j++) {
+    const int k0 = (j * 32 + lane) * 8;
+    if (k0 >= K) continue;
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv[j]);
 #pragma unroll
     for (int b = 0; b < 16; b++) {
       if (b < Bm) {
-        float2 v = __half22float2(reinterpret_cast<const __half2*>(x + (size_t)b * K)[k]);
-        if (silu_in) { v.x = silu(v.x); v.y = silu(v.y); }
-        acc[b] += v.x * w.x + v.y * w.y;
+        const uint4 xv = *reinterpret_cast<const uint4*>(s_x + (size_t)b * K + k0);
+        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const float2 a = __half22float2(xh[t]), w = __half22float2(wh[t]);
+          acc[b] += a.x * w.x + a.y * w.y;
+        }
       }
     }
   }
@@ -367,6 +387,50 @@ __global__ void k_sds_grad(const float* __restrict__ eps, const float* __restric
   grad[i] = w[b] * (np - noise[i]);
 }
 
+// Linear stand-in for the VAE encoder (the VAE is outside this build):
+// latents[b,k,y,x] = sum_c mix[k][c] * mean_{8x8}(2*color[b,c]-1); and its exact transpose.
+__global__ void k_pool_latents(const float* __restrict__ color, const float* __restrict__ mix, float* __restrict__ lat,
+                               int B, int H, int W) {
+  const int Ho = H >> 3, Wo = W >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Ho * Wo) return;
+  const int ox = i % Wo, oy = (i / Wo) % Ho, b = i / (Wo * Ho);
+  float m[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float s = 0.f;
+    const float* src = color + (((size_t)b * 3 + c) * H + oy * 8) * W + ox * 8;
+    for (int dy = 0; dy < 8; dy++) {
+      const float4 u = *reinterpret_cast<const float4*>(src + (size_t)dy * W);
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)dy * W + 4);
+      s += u.x + u.y + u.z + u.w + v.x + v.y + v.z + v.w;
+    }
+    m[c] = 2.0f * (s * (1.0f / 64.0f)) - 1.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    lat[(((size_t)b * 4 + k) * Ho + oy) * Wo + ox] = mix[k * 3] * m[0] + mix[k * 3 + 1] * m[1] + mix[k * 3 + 2] * m[2];
+}
+// dL/dcolor from dL/dlatents (nan_to_num + clamp first, stable_diffusion_guidance.py:418-421),
+// scaled by 1/B like loss_sds (:427).
+__global__ void k_pool_latents_bwd(const float* __restrict__ grad, const float* __restrict__ mix, float* __restrict__ dcolor,
+                                   int B, int H, int W, float clip, float scale) {
+  const int Ho = H >> 3, Wo = W >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * 3 * H * W) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % 3), b = (int)(i / ((long long)3 * W * H));
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float g = grad[(((size_t)b * 4 + k) * Ho + (y >> 3)) * Wo + (x >> 3)];
+    if (!(g == g)) g = 0.f;                          // nan_to_num
+    g = fminf(fmaxf(g, -3.4028235e38f), 3.4028235e38f);
+    if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
+    acc += mix[k * 3 + c] * g;
+  }
+  dcolor[i] = acc * (2.0f / 64.0f) * scale;
+}
+
 }  // namespace gdu
 
 extern "C" {
@@ -389,12 +453,22 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     return fail(GD_UNET_ERR_INVALID_ARG, "gemm: GEGLU epilogue needs N % 32 == 0 and no residual/transposition");
   int BN = a->block_n;
   if (BN <= 0) {
-    if (a->N <= 256) BN = (a->N + 15) / 16 * 16;
+    const int geglu = (a->flags & GD_EPI_GEGLU) ? 1 : 0;
+    const long long mt = ((long long)a->M + gdu::kBM - 1) / gdu::kBM * a->batch;
+    if (a->N <= 128) BN = (a->N + 15) / 16 * 16;
     else {
-      const int cands[] = {256, 192, 160, 128};
-      BN = 128;
-      for (int c : cands) if (a->N % c == 0) { BN = c; break; }
+      // largest tile that still yields >= ~1 wave of CTAs over 148 SMs; wide tiles amortise A
+      const int cands[] = {256, 192, 160, 128, 96, 64};
+      BN = 64;
+      for (int c : cands) {
+        if (geglu && c % 32) continue;
+        if (a->N % c && !(c == 128 || c == 64)) continue;   // ragged N only with 128 / 64
+        const long long ctas = mt * ((a->N + c - 1) / c);
+        if (ctas >= 140 || c == 64) { BN = c; break; }
+      }
+      if (a->N <= 256 && BN > a->N) BN = (a->N + 15) / 16 * 16;
     }
+    if (geglu && BN % 32) BN = (BN + 31) / 32 * 32;
   }
   if (BN % 16 || BN < 16 || BN > 256 || ((a->flags & GD_EPI_GEGLU) && BN % 32))
     return fail(GD_UNET_ERR_INVALID_ARG, "gemm: block_n must be a multiple of 16 in 16..256");
@@ -555,9 +629,12 @@ int gd_unet_concat(const void* a, const void* b, void* y, long long rows, int Ca
 }
 int gd_unet_small_linear(const void* x, const void* W, const void* bias, void* y, int Bm, int K, int N, int silu_in,
                          int silu_out, gd_ustream_t s) {
-  if (Bm < 1 || Bm > 16 || K % 2) return fail(GD_UNET_ERR_INVALID_ARG, "small_linear: 1 <= Bm <= 16, even K");
-  gdu::k_small_linear<<<(N + 7) / 8, 256, 0, (cudaStream_t)s>>>((const __half*)x, (const __half*)W, (const __half*)bias,
-                                                               (__half*)y, Bm, K, N, silu_in, silu_out);
+  if (Bm < 1 || Bm > 16 || K % 8 || K > 2048) return fail(GD_UNET_ERR_INVALID_ARG, "small_linear: 1 <= Bm <= 16, K % 8 == 0, K <= 2048");
+  const size_t smem = (size_t)Bm * K * 2;
+  const dim3 grid((N + 7) / 8);
+#define GD_SL(KV) gdu::k_small_linear<KV><<<grid, 256, smem, (cudaStream_t)s>>>((const __half*)x, (const __half*)W, (const __half*)bias, (__half*)y, Bm, K, N, silu_in, silu_out)
+  if (K <= 512) GD_SL(2); else if (K <= 1280) GD_SL(5); else GD_SL(8);
+#undef GD_SL
   LAUNCH_CHECK("k_small_linear");
   return GD_UNET_OK;
 }
@@ -585,6 +662,21 @@ int gd_unet_add_noise(const float* lat, const float* noise, const float* sa, con
                       int reps, int chw, gd_ustream_t s) {
   gdu::k_add_noise<<<(B * chw + 255) / 256, 256, 0, (cudaStream_t)s>>>(lat, noise, sa, sb, noisy, (__half*)uin, B, reps, chw);
   LAUNCH_CHECK("k_add_noise");
+  return GD_UNET_OK;
+}
+int gd_unet_pool_latents(const float* color, const float* mix, float* latents, int B, int H, int W, gd_ustream_t s) {
+  if (H % 8 || W % 8) return fail(GD_UNET_ERR_INVALID_ARG, "pool_latents: H, W multiples of 8");
+  const int n = B * (H / 8) * (W / 8);
+  gdu::k_pool_latents<<<(n + 127) / 128, 128, 0, (cudaStream_t)s>>>(color, mix, latents, B, H, W);
+  LAUNCH_CHECK("k_pool_latents");
+  return GD_UNET_OK;
+}
+int gd_unet_pool_latents_bwd(const float* grad, const float* mix, float* dcolor, int B, int H, int W, float clip, float scale,
+                             gd_ustream_t s) {
+  if (H % 8 || W % 8) return fail(GD_UNET_ERR_INVALID_ARG, "pool_latents_bwd: H, W multiples of 8");
+  const long long n = (long long)B * 3 * H * W;
+  gdu::k_pool_latents_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(grad, mix, dcolor, B, H, W, clip, scale);
+  LAUNCH_CHECK("k_pool_latents_bwd");
   return GD_UNET_OK;
 }
 int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float gs, float* np, float* grad, int B, int chw,

@@ -1,0 +1,94 @@
+"""One SDS step on rendered views, as bench.py times it (BASELINE config 2 with the VAE excluded):
+
+    colour [B,3,S,S] --(linear stand-in for the VAE encoder)--> latents [B,4,S/8,S/8]
+      --> StableDiffusionGuidance.compute_grad_sds (B200 UNet, batch 2B) --> grad
+      --> nan_to_num / clamp / 1/B (guidance __call__, :418-427) --> dL/dcolour [B,3,S,S]
+
+The stand-in (8x8 mean of 2*rgb-1 and a fixed 3->4 channel mix) is NOT the reference's VAE; the
+VAE encoder is row f1 ("next") of SURVEY.md s.8 and every number produced through this module says
+"VAE excluded" in its config.
+"""
+import torch
+
+from . import unet_ops as ops
+from .guidance import PromptProcessorOutput, StableDiffusionGuidance
+from .unet import UNetB200
+
+UNET_FLOPS_PER_SAMPLE = 804.3e9  # SURVEY.md Appendix B (conv 418.4 + linear 259.8 + attention 126.1 GFLOP)
+
+
+def _random_state_dict(seed, device):
+    from .unet_init import random_state_dict
+    return random_state_dict(seed, device, torch.float16)
+
+
+class SdsBenchStep:
+    def __init__(self, dev, views, state_dict=None, seed=0, use_cuda_graph=True):
+        self.dev = torch.device(dev)
+        self.B = views
+        sd = state_dict if state_dict is not None else _random_state_dict(seed, self.dev)
+        self.unet = UNetB200(sd, self.dev, use_cuda_graph=use_cuda_graph)
+        g = torch.Generator().manual_seed(1234 + seed)
+        bank = lambda n: torch.randn(n, 77, 1024, generator=g).to(self.dev)
+        self.prompt = PromptProcessorOutput(bank(1), bank(1), bank(4), bank(4))
+        self.gen = torch.Generator(device=self.dev).manual_seed(99 + seed)
+        self.guidance = StableDiffusionGuidance(self.unet, self.dev, generator=self.gen)
+        self.guidance.grad_clip_val = 1.5
+        self.mix = (torch.tensor([[0.6, 0.3, 0.1], [-0.3, 0.5, -0.2], [0.2, -0.4, 0.6], [0.3, 0.3, -0.6]]) * 2.0).to(self.dev).contiguous()
+        self._launch0 = ops.lib().gd_unet_launch_count()
+        self._unet_ms = []
+        self.last_grad = None
+
+    def image_grad(self, color, cams):
+        """color [B,3,S,S] fp32 (rasteriser output) -> dL_sds/dcolor [B,3,S,S] fp32."""
+        B, _, H, W = color.shape
+        L = ops.lib()
+        stream = torch.cuda.current_stream().cuda_stream
+        lat = torch.empty((B, 4, H // 8, W // 8), dtype=torch.float32, device=color.device)
+        ops._chk(L.gd_unet_pool_latents(color.data_ptr(), self.mix.data_ptr(), lat.data_ptr(), B, H, W, stream), "pool_latents")
+        t = torch.randint(self.guidance.min_step, self.guidance.max_step + 1, [B], dtype=torch.long, device=color.device,
+                          generator=self.gen)
+        elev = torch.tensor([c.elevation_deg for c in cams], device=color.device)
+        azim = torch.tensor([c.azimuth_deg for c in cams], device=color.device)
+        dist = torch.tensor([c.distance for c in cams], device=color.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        grad, _ = self.guidance.compute_grad_sds(lat, t, self.prompt, elev, azim, dist)
+        e1.record()
+        self._unet_ms.append((e0, e1))
+        self.last_grad = grad
+        dcol = torch.empty_like(color)
+        ops._chk(L.gd_unet_pool_latents_bwd(grad.data_ptr(), self.mix.data_ptr(), dcol.data_ptr(), B, H, W,
+                                            float(self.guidance.grad_clip_val or 0.0), 1.0 / B, stream), "pool_latents_bwd")
+        return dcol
+
+    def reset_counters(self):
+        self._launch0 = ops.lib().gd_unet_launch_count()
+        self._unet_ms = []
+
+    def launch_count_delta(self):
+        """Kernels of libgd_unet.so launched since reset; a CUDA-graph replay re-launches the
+        captured kernels without passing through the C ABI, so those are counted from the graph."""
+        direct = ops.lib().gd_unet_launch_count() - self._launch0
+        return int(direct + self.unet.graph_kernel_launches_since_reset())
+
+    def compute_grad_ms(self):
+        return float(sum(a.elapsed_time(b) for a, b in self._unet_ms) / max(1, len(self._unet_ms)))
+
+    def roofline(self, peaks, peak_kind, raster_bwd=None):
+        ms = self.compute_grad_ms()
+        flops = UNET_FLOPS_PER_SAMPLE * 2 * self.B
+        achieved = flops / (ms * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        r = {"bound": "tensor", "kernel": "compute_grad_sds = UNet forward batch 2B (k_gemm_tcgen05 + k_flash_attn "
+                                          "carry ~85% of its time, profiles/) + noise/SDS epilogue kernels",
+             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+             "peak_source": peak_kind + " (sustained cuBLAS bf16; fp16 tcgen05 has the same peak)",
+             "algorithmic_flops": flops, "launch_ms": ms}
+        if raster_bwd is not None:
+            r["raster_bwd"] = raster_bwd
+        return r
+
+
+def make_bench_guidance(dev, views):
+    return SdsBenchStep(dev, views)

@@ -38,6 +38,7 @@ class UNetB200:
             self.w[k] = self._convert(k, v)
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        self._graph_launches = 0
         self.dtype = torch.float16
         self.training = False
 
@@ -160,12 +161,21 @@ class UNetB200:
                 self._forward_impl(g.sample, g.t, g.ctx)
             torch.cuda.current_stream().wait_stream(side)
             g.graph = torch.cuda.CUDAGraph()
+            n0 = ops.lib().gd_unet_launch_count()
             with torch.cuda.graph(g.graph):
                 g.out = self._forward_impl(g.sample, g.t, g.ctx)
+            g.kernels = int(ops.lib().gd_unet_launch_count() - n0)  # kernels captured in the graph
             self._graphs[key] = g
         g.sample.copy_(sample); g.t.copy_(t_f32); g.ctx.copy_(ctx)
         g.graph.replay()
+        self._graph_launches += g.kernels
         return g.out
+
+    def graph_kernel_launches_since_reset(self, reset=True):
+        n = self._graph_launches
+        if reset:
+            self._graph_launches = 0
+        return n
 
     def __call__(self, sample, timestep, encoder_hidden_states=None, **kwargs):
         out = self.forward_f32(sample, timestep, encoder_hidden_states)

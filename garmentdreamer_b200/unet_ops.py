@@ -65,8 +65,11 @@ def lib():
         L.gd_unet_conv_out.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
         L.gd_unet_add_noise.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
         L.gd_unet_sds_grad.argtypes = [vp, vp, vp, f, vp, vp, i, i, vp]
+        L.gd_unet_pool_latents.argtypes = [vp, vp, vp, i, i, i, vp]
+        L.gd_unet_pool_latents_bwd.argtypes = [vp, vp, vp, i, i, i, f, f, vp]
         for name in ("gemm", "flash_attn", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
-                     "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad"):
+                     "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad",
+                     "pool_latents", "pool_latents_bwd"):
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
         _unet = L
     return _unet

@@ -124,6 +124,15 @@ int gd_unet_add_noise(const float* latents, const float* noise, const float* sqr
 int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float guidance_scale,
                      float* noise_pred, float* grad, int B, int chw, gd_ustream_t stream);
 
+/* Bench glue, NOT part of the reference path: a fixed linear stand-in for the VAE encoder that
+   the reference runs between the rasteriser and compute_grad_sds (encode_images, :160-167; out of
+   this build's scope). latents [B,4,H/8,W/8] = mix[4][3] * mean_8x8(2*color-1); _bwd is its exact
+   transpose applied to nan_to_num(clamp(grad, +-clip)) * scale (clip <= 0: no clamp). */
+int gd_unet_pool_latents(const float* color_nchw, const float* mix, float* latents, int B, int H, int W,
+                         gd_ustream_t stream);
+int gd_unet_pool_latents_bwd(const float* grad, const float* mix, float* dcolor_nchw, int B, int H, int W,
+                             float clip, float scale, gd_ustream_t stream);
+
 const char* gd_unet_last_error(void);
 uint64_t gd_unet_launch_count(void);
 const char* gd_unet_version(void);
