@@ -25,7 +25,8 @@ namespace gdu {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;   // 64 fp16 = 128 bytes = one swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // producer + issuer + epilogue warps
 
 struct GemmKParams {
   int M, N, num_kb, kb_per_tap;
@@ -42,6 +43,7 @@ struct GemmKParams {
   unsigned flags;
   int block_n;
   int stages;
+  int m_tiles, n_tiles, total_tiles;
 };
 
 __device__ __forceinline__ uint32_t s2u(const void* p) {
@@ -98,7 +100,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-__global__ void __launch_bounds__(kGemmThreads, 2)
+// Persistent, warp-specialised: grid = min(tiles, SMs). The accumulator is double-buffered in
+// TMEM so the epilogue of tile i overlaps the main loop of tile i+1; the TMA ring runs ahead
+// across tile boundaries. 10 warps: 0 = TMA producer, 1 = MMA issuer (+TMEM owner), 2..9 =
+// epilogue (two warps per TMEM lane quarter, each takes half of the tile's 32-column chunks).
+__global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,24 +113,24 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + S;
-  uint64_t* tmem_full = empty + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + S;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x, n_blk = blockIdx.y, z = blockIdx.z;
-  const int zh = z % p.heads, zb = z / p.heads;
-  const uint32_t tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  const uint32_t acc_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // per accumulator
+  const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, total = p.total_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < S; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
-    bar_init(tmem_full, 1);
+    for (int s = 0; s < 2; s++) { bar_init(&tmem_full[s], 1); bar_init(&tmem_empty[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(2 * acc_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -135,124 +141,172 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      int a_c1, a_c2, a_c3;
-      if (p.mode_conv) {
-        const int tile_rows = p.rows_box * p.img_w;             // pixels per image in this tile
-        const int tiles_per_img = p.rows_per_image / tile_rows; // >= 1 when imgs_box == 1
-        if (p.imgs_box == 1) { a_c3 = m_blk / tiles_per_img; a_c2 = (m_blk % tiles_per_img) * p.rows_box; }
-        else { a_c3 = m_blk * p.imgs_box; a_c2 = 0; }
-        a_c1 = 0;
-      } else {
-        a_c1 = m_blk * kBM; a_c2 = p.a_zflat ? z : zb; a_c3 = 0;
-      }
-      const int b_c1 = n_blk * BN + zh * p.b_head_n;
-      for (int kb = 0; kb < p.num_kb; kb++) {
-        const int s = kb % S;
-        bar_wait(&empty[s], ((kb / S) & 1) ^ 1);
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        bar_expect_tx(&full[s], a_bytes + b_bytes);
+      int it = 0;  // ring position, runs across tiles
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n_blk = t % n_tiles, m_blk = (t / n_tiles) % m_tiles, z = t / (n_tiles * m_tiles);
+        const int zh = z % p.heads, zb = z / p.heads;
+        int a_c1, a_c2, a_c3;
         if (p.mode_conv) {
-          const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
-          tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+          const int tile_rows = p.rows_box * p.img_w;
+          const int tiles_per_img = p.rows_per_image / tile_rows;
+          if (p.imgs_box == 1) { a_c3 = m_blk / tiles_per_img; a_c2 = (m_blk % tiles_per_img) * p.rows_box; }
+          else { a_c3 = m_blk * p.imgs_box; a_c2 = 0; }
+          a_c1 = 0;
         } else {
-          tma_load_4d(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
+          a_c1 = m_blk * kBM; a_c2 = p.a_zflat ? z : zb; a_c3 = 0;
         }
-        tma_load_3d(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, p.b_zdim > 1 ? zb : 0);
+        const int b_c1 = n_blk * BN + zh * p.b_head_n;
+        const int b_c2 = p.b_zdim > 1 ? zb : 0;
+        for (int kb = 0; kb < p.num_kb; kb++, it++) {
+          const int s = it % S;
+          bar_wait(&empty[s], ((it / S) & 1) ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          bar_expect_tx(&full[s], a_bytes + b_bytes);
+          if (p.mode_conv) {
+            const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
+            tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+          } else {
+            tma_load_4d(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
+          }
+          tma_load_3d(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, b_c2);
+        }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = umma_idesc_f16(BN);
-    for (int kb = 0; kb < p.num_kb; kb++) {
-      const int s = kb % S;
-      bar_wait(&full[s], (kb / S) & 1);
+    int it = 0, lt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
+      const int acc = lt & 1;
+      bar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
-        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
+      for (int kb = 0; kb < p.num_kb; kb++, it++) {
+        const int s = it % S;
+        bar_wait(&full[s], (it / S) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; k++)  // +32 B per K=16 step inside the 128 B swizzle row
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(&empty[s]);                       // slot free once these MMAs have read it
-        if (kb == p.num_kb - 1) umma_commit(tmem_full);  // accumulator complete
+          for (int k = 0; k < kBK / 16; k++)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);                                   // slot free once these MMAs read it
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);     // accumulator complete
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ---------------- epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) ----------------
-    const int q = warp & 3;
-    bar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m_blk * kBM + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;
-    const int img = p.rows_per_image > 0 ? row / p.rows_per_image : 0;
+    // ---------------- epilogue: warps 2..9; quarter q = warp & 3, column half = (warp - 2) >> 2 ----
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const bool geglu = p.flags & GD_EPI_GEGLU, transposed = p.flags & GD_EPI_TRANSPOSED;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int n0 = n_blk * BN + c0;
-      if (!row_ok || n0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int n = n0 + j;
-        float x = __uint_as_float(r[j]) * p.alpha;
-        if (n < p.N) {
-          if (p.bias) x += __half2float(p.bias[n]);
-          if (p.row_bias) x += __half2float(p.row_bias[(long long)img * p.N + n]);
+    const int chunks = (BN + 31) / 32;
+    int lt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
+      const int n_blk = t % n_tiles, m_blk = (t / n_tiles) % m_tiles, z = t / (n_tiles * m_tiles);
+      const int zh = z % p.heads, zb = z / p.heads;
+      const int acc = lt & 1;
+      const int row = m_blk * kBM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;
+      const int img = p.rows_per_image > 0 ? row / p.rows_per_image : 0;
+      bar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = half; c < chunks; c += 2) {
+        const int c0 = c * 32;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 2 >= chunks) {  // last TMEM read of this warp for the tile: release the accumulator
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
         }
-        v[j] = x;
-      }
-      if (geglu) {  // columns come as 16 values followed by their 16 gates
-        __half* dst = p.C + coff + (long long)row * p.ldc + (n0 >> 1);
-        __align__(16) __half o[16];
+        const int n0 = n_blk * BN + c0;
+        if (!row_ok || n0 >= p.N) continue;
+        const bool full32 = n0 + 32 <= p.N;
+        float v[32];
+        if (p.bias && full32) {
+          __align__(16) __half bb[32];
 #pragma unroll
-        for (int j = 0; j < 16; j++) o[j] = __float2half_rn(v[j] * gelu_erf(v[16 + j]));
-        if (n0 + 32 <= p.N) {
-          reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
-          reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
-        }
-      } else if (transposed) {
+          for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(bb)[u] = reinterpret_cast<const uint4*>(p.bias + n0)[u];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int n = n0 + j;
-          if (n < p.N) p.C[coff + (long long)n * p.ldc + row] = __float2half_rn(v[j]);
-        }
-      } else {
-        __half* dst = p.C + coff + (long long)row * p.ldc + n0;
-        const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
-        if (n0 + 32 <= p.N && (p.ldc & 7) == 0) {
-          __align__(16) __half o[32];
-          if (res) {
-            __align__(16) __half rr[32];
-#pragma unroll
-            for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(rr)[u] = reinterpret_cast<const uint4*>(res)[u];
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] += __half2float(rr[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j++) o[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(v[j]) : v[j]);
-#pragma unroll
-          for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) * p.alpha + __half2float(bb[j]);
         } else {
+#pragma unroll
           for (int j = 0; j < 32; j++) {
-            if (n0 + j < p.N) {
-              float x = v[j] + (res ? __half2float(res[j]) : 0.0f);
-              dst[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(x) : x);
+            float x = __uint_as_float(r[j]) * p.alpha;
+            if (p.bias && n0 + j < p.N) x += __half2float(p.bias[n0 + j]);
+            v[j] = x;
+          }
+        }
+        if (p.row_bias) {
+          const __half* rb = p.row_bias + (long long)img * p.N + n0;
+          if (full32) {
+            __align__(16) __half bb[32];
+#pragma unroll
+            for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(bb)[u] = reinterpret_cast<const uint4*>(rb)[u];
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] += __half2float(bb[j]);
+          } else {
+            for (int j = 0; j < 32; j++) if (n0 + j < p.N) v[j] += __half2float(rb[j]);
+          }
+        }
+        if (geglu) {  // columns come as 16 values followed by their 16 gates
+          __half* dst = p.C + coff + (long long)row * p.ldc + (n0 >> 1);
+          __align__(16) __half o[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) o[j] = __float2half_rn(v[j] * gelu_erf(v[16 + j]));
+          if (full32) {
+            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
+            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
+          }
+        } else if (transposed) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int n = n0 + j;
+            if (n < p.N) p.C[coff + (long long)n * p.ldc + row] = __float2half_rn(v[j]);
+          }
+        } else {
+          __half* dst = p.C + coff + (long long)row * p.ldc + n0;
+          const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
+          if (full32 && (p.ldc & 7) == 0) {
+            __align__(16) __half o[32];
+            if (res) {
+              __align__(16) __half rr[32];
+#pragma unroll
+              for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(rr)[u] = reinterpret_cast<const uint4*>(res)[u];
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] += __half2float(rr[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) o[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(v[j]) : v[j]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
+          } else {
+            for (int j = 0; j < 32; j++) {
+              if (n0 + j < p.N) {
+                float x = v[j] + (res ? __half2float(res[j]) : 0.0f);
+                dst[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(x) : x);
+              }
             }
           }
         }
+      }
+      if (half >= chunks) {  // this warp had no chunk in the tile (BN <= 32): still release it
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
       }
     }
   }
@@ -260,7 +314,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
   }
 }
 

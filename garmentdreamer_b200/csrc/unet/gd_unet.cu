@@ -453,20 +453,24 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     return fail(GD_UNET_ERR_INVALID_ARG, "gemm: GEGLU epilogue needs N % 32 == 0 and no residual/transposition");
   int BN = a->block_n;
   if (BN <= 0) {
+    // persistent grid of 148 CTAs: trade wave quantisation against tile width (arithmetic intensity)
     const int geglu = (a->flags & GD_EPI_GEGLU) ? 1 : 0;
     const long long mt = ((long long)a->M + gdu::kBM - 1) / gdu::kBM * a->batch;
-    if (a->N <= 128) BN = (a->N + 15) / 16 * 16;
+    if (a->N <= 64) BN = (a->N + 15) / 16 * 16;
     else {
-      // largest tile that still yields >= ~1 wave of CTAs over 148 SMs; wide tiles amortise A
-      const int cands[] = {256, 192, 160, 128, 96, 64};
+      const int cands[] = {256, 192, 160, 128, 96, 80, 64};
+      double best = -1.0;
       BN = 64;
       for (int c : cands) {
         if (geglu && c % 32) continue;
+        if (c > ((a->N + 15) / 16 * 16)) continue;
         if (a->N % c && !(c == 128 || c == 64)) continue;   // ragged N only with 128 / 64
-        const long long ctas = mt * ((a->N + c - 1) / c);
-        if (ctas >= 140 || c == 64) { BN = c; break; }
+        const long long tiles = mt * ((a->N + c - 1) / c);
+        const long long waves = (tiles + 147) / 148;
+        const double score = ((double)tiles / (double)(waves * 148)) * ((double)c / (double)(c + 128));
+        if (score > best) { best = score; BN = c; }
       }
-      if (a->N <= 256 && BN > a->N) BN = (a->N + 15) / 16 * 16;
+      if (a->N <= 256 && a->N % 16 == 0 && mt >= 148) BN = a->N;  // one n-tile when M alone fills the GPU
     }
     if (geglu && BN % 32) BN = (BN + 31) / 32 * 32;
   }
@@ -507,20 +511,23 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
-  // <= ~110 KB per CTA so that two CTAs share an SM: one's epilogue overlaps the other's main loop
-  int stages = (int)((108 * 1024) / stage_bytes);
-  if (stages > 6) stages = 6;
+  int stages = (int)((200 * 1024) / stage_bytes);   // one persistent CTA per SM owns the shared memory
+  if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
   p.stages = stages;
+  p.m_tiles = (a->M + gdu::kBM - 1) / gdu::kBM;
+  p.n_tiles = (a->N + BN - 1) / BN;
+  p.total_tiles = p.m_tiles * p.n_tiles * a->batch;
   const size_t smem = stages * stage_bytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaFuncSetAttribute(gdu::k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
-    attr_set = true;
   }
-  dim3 grid((a->M + gdu::kBM - 1) / gdu::kBM, (a->N + BN - 1) / BN, a->batch);
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   gdu::k_gemm_tcgen05<<<grid, gdu::kGemmThreads, smem, stream>>>(tmA, tmB, p);
   LAUNCH_CHECK("k_gemm_tcgen05");
   return GD_UNET_OK;
