@@ -233,8 +233,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
         }
         const int n0 = n_blk * BN + c0;
-        if (!row_ok || n0 >= p.N) continue;
-        const bool full32 = n0 + 32 <= p.N;
+        const int nlim = min(p.N, (n_blk + 1) * BN);  // columns of this tile that exist
+        if (!row_ok || n0 >= nlim) continue;
+        const bool full32 = n0 + 32 <= nlim;
         float v[32];
         if (p.bias && full32) {
           __align__(16) __half bb[32];
@@ -246,7 +247,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             float x = __uint_as_float(r[j]) * p.alpha;
-            if (p.bias && n0 + j < p.N) x += __half2float(p.bias[n0 + j]);
+            if (p.bias && n0 + j < nlim) x += __half2float(p.bias[n0 + j]);
             v[j] = x;
           }
         }
@@ -259,7 +260,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] += __half2float(bb[j]);
           } else {
-            for (int j = 0; j < 32; j++) if (n0 + j < p.N) v[j] += __half2float(rb[j]);
+            for (int j = 0; j < 32; j++) if (n0 + j < nlim) v[j] += __half2float(rb[j]);
           }
         }
         if (geglu) {  // columns come as 16 values followed by their 16 gates
@@ -275,7 +276,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             const int n = n0 + j;
-            if (n < p.N) p.C[coff + (long long)n * p.ldc + row] = __float2half_rn(v[j]);
+            if (n < nlim) p.C[coff + (long long)n * p.ldc + row] = __float2half_rn(v[j]);
           }
         } else {
           __half* dst = p.C + coff + (long long)row * p.ldc + n0;
@@ -295,7 +296,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
           } else {
             for (int j = 0; j < 32; j++) {
-              if (n0 + j < p.N) {
+              if (n0 + j < nlim) {
                 float x = v[j] + (res ? __half2float(res[j]) : 0.0f);
                 dst[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(x) : x);
               }
