@@ -4,8 +4,9 @@
 //   warp 0    : TMA producer (Q once; K tiles twice; V^T tiles once)
 //   warp 1    : tcgen05.mma issuer  S = Q K_j^T  (M128 N128 K64, TMEM, double buffered)
 //                                   O += P_j V_j (M128 N64  K128, TMEM)
-//   warps 2-5 : softmax: tcgen05.ld S, P = exp2((S - m) * c) -> fp16 -> shared memory in the
-//               128B-swizzled K-major layout the MMA reads as its A operand
+//   warps 2-9 : softmax: tcgen05.ld S, P = exp2((S - m) * c) -> fp16 -> shared memory in the
+//               128B-swizzled K-major layout the MMA reads as its A operand. Two warps share a
+//               TMEM lane quarter and split each 128-key tile into its two 64-key blocks.
 // Two passes over the keys: pass 1 only reduces the row maxima m (no exp), pass 2 recomputes S and
 // accumulates O and the row sums with the FINAL maximum, so O never needs rescaling in TMEM.
 // The S matrix (1.3 GB per 64x64 layer at batch 8) never touches HBM.
@@ -22,7 +23,7 @@ struct AttnParams {
   long long ldo;
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 64 + 8 * 32;  // producer, issuer, 8 softmax warps (2 per TMEM lane quarter)
 constexpr uint32_t kQBytes = 128 * 64 * 2, kKBytes = 128 * 64 * 2, kVBytes = 2 * 64 * 64 * 2, kPBytes = 2 * 128 * 64 * 2;
 
 __device__ __forceinline__ void bar_arrive(uint64_t* b) {
@@ -73,8 +74,8 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     for (int s = 0; s < 2; s++) {
       bar_init(&k_full[s], 1); bar_init(&k_empty[s], 1);
       bar_init(&v_full[s], 1); bar_init(&v_empty[s], 1);
-      bar_init(&s_full[s], 1); bar_init(&s_empty[s], 4);   // one arrive per softmax warp
-      bar_init(&p_full[s], 4); bar_init(&p_empty[s], 1);
+      bar_init(&s_full[s], 1); bar_init(&s_empty[s], 8);   // one arrive per softmax warp
+      bar_init(&p_full[s], 8); bar_init(&p_empty[s], 1);
     }
     bar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,59 +152,72 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
   } else {
     const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int hb = (warp - 2) >> 2;               // which 64-key block of every tile this warp owns
     const int r = q * 32 + lane;                  // row inside the 128-row tile
     const int row = m_blk * 128 + r;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* s_x = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128] exchange between the two halves
     float m = -INFINITY, l = 0.f;
     for (int i = 0; i < iters; i++) {
       const int j = i % n, s = i & 1;
-      const int kmax = p.Tk - j * 128;            // keys >= kmax in this tile are padding
+      const int kmax = p.Tk - j * 128 - hb * 64;  // keys >= kmax in this warp's block are padding
       bar_wait(&s_full[s], (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (i < n) {
-        // ---- pass 1: row maximum ----
+        // ---- pass 1: row maximum over this warp's 64 keys ----
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < 2; c++) {
           uint32_t v[32];
-          tmem_ld32(tmem_S0 + s * 128 + lane_base + c * 32, v);
+          tmem_ld32(tmem_S0 + s * 128 + lane_base + hb * 64 + c * 32, v);
+          if (kmax >= 64) {
 #pragma unroll
-          for (int t = 0; t < 32; t++)
-            if (c * 32 + t < kmax) m = fmaxf(m, __uint_as_float(v[t]));
+            for (int t = 0; t < 32; t++) m = fmaxf(m, __uint_as_float(v[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; t++)
+              if (c * 32 + t < kmax) m = fmaxf(m, __uint_as_float(v[t]));
+          }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) bar_arrive(&s_empty[s]);
+        if (i == n - 1) {  // combine the maxima of the two key halves (softmax warps only: barrier 1)
+          s_x[hb * 128 + r] = m;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          m = fmaxf(m, s_x[(hb ^ 1) * 128 + r]);
+        }
       } else {
-        // ---- pass 2: P = exp2((S - m) * c), row sums, P -> shared memory (A operand of P V) ----
+        // ---- pass 2: P = exp2(S*c - m*c), row sums, P -> shared memory (A operand of P V) ----
         const int vi = i - n, ps = vi & 1;
         bar_wait(&p_empty[ps], ((vi >> 1) & 1) ^ 1);
         const float mc = m * p.scale_log2e;
-        uint8_t* prow = sP + ps * kPBytes + r * 128;
+        uint8_t* blk = sP + ps * kPBytes + hb * (128 * 64 * 2) + r * 128;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < 2; c++) {
           uint32_t v[32];
-          tmem_ld32(tmem_S0 + s * 128 + lane_base + c * 32, v);
-          if (c == 3) {  // all TMEM reads of this S buffer are done
+          tmem_ld32(tmem_S0 + s * 128 + lane_base + hb * 64 + c * 32, v);
+          if (c == 1) {  // all TMEM reads of this S buffer by this warp are done
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(&s_empty[s]);
           }
-          uint8_t* blk = prow + (c >> 1) * (128 * 64 * 2);   // key block 0/1 of the tile
 #pragma unroll
           for (int g = 0; g < 4; g++) {                       // 4 chunks of 8 keys = 16 bytes
             __align__(16) __half2 hv[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-              const int k0 = c * 32 + g * 8 + 2 * t;
-              float e0 = exp2f(__uint_as_float(v[g * 8 + 2 * t]) * p.scale_log2e - mc);
-              float e1 = exp2f(__uint_as_float(v[g * 8 + 2 * t + 1]) * p.scale_log2e - mc);
-              if (k0 >= kmax) e0 = 0.f;
-              if (k0 + 1 >= kmax) e1 = 0.f;
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[g * 8 + 2 * t]), p.scale_log2e, -mc)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[g * 8 + 2 * t + 1]), p.scale_log2e, -mc)));
+              if (kmax < 64) {
+                const int k0 = c * 32 + g * 8 + 2 * t;
+                if (k0 >= kmax) e0 = 0.f;
+                if (k0 + 1 >= kmax) e1 = 0.f;
+              }
+              l += e0 + e1;
               hv[t] = __floats2half2_rn(e0, e1);
-              const float2 back = __half22float2(hv[t]);    // sum what the MMA will actually see
-              l += back.x + back.y;
             }
-            const int chunk = (c & 1) * 4 + g;               // 16-byte chunk index in the 128 B row
+            const int chunk = c * 4 + g;                       // 16-byte chunk index in the 128 B row
             *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(hv);
           }
         }
@@ -212,21 +226,24 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (lane == 0) bar_arrive(&p_full[ps]);
       }
     }
-    // ---- epilogue: O / l ----
+    // ---- epilogue: O / l; the two warps of a quarter take 32 of the 64 output columns each ----
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has read the pass-1 exchange
+    s_x[hb * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += s_x[(hb ^ 1) * 128 + r];
     bar_wait(o_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float inv = 1.0f / l;
-    __half* dst = p.O + ((long long)b * p.Tq + row) * p.ldo + h * 64;
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
+    __half* dst = p.O + ((long long)b * p.Tq + row) * p.ldo + h * 64 + hb * 32;
+    {
       uint32_t v[32];
-      tmem_ld32(tmem_O + lane_base + c * 32, v);
+      tmem_ld32(tmem_O + lane_base + hb * 32, v);
       if (row < p.Tq) {
         __align__(16) __half o[32];
 #pragma unroll
         for (int t = 0; t < 32; t++) o[t] = __float2half_rn(__uint_as_float(v[t]) * inv);
 #pragma unroll
-        for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst + c * 32)[u] = reinterpret_cast<const uint4*>(o)[u];
+        for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
       }
     }
   }

@@ -44,6 +44,8 @@ struct GemmKParams {
   int block_n;
   int stages;
   int m_tiles, n_tiles, total_tiles;
+  int ksplit, kb_per_split;   // split-K: tile t covers k-blocks [ks*kb_per_split, ...) and writes fp32 partials
+  float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
 };
 
 __device__ __forceinline__ uint32_t s2u(const void* p) {
@@ -143,8 +145,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- TMA producer ----------------
       int it = 0;  // ring position, runs across tiles
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int n_blk = t % n_tiles, m_blk = (t / n_tiles) % m_tiles, z = t / (n_tiles * m_tiles);
+        const int ks = t % p.ksplit, tt = t / p.ksplit;
+        const int n_blk = tt % n_tiles, m_blk = (tt / n_tiles) % m_tiles, z = tt / (n_tiles * m_tiles);
         const int zh = z % p.heads, zb = z / p.heads;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         int a_c1, a_c2, a_c3;
         if (p.mode_conv) {
           const int tile_rows = p.rows_box * p.img_w;
@@ -157,7 +161,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int b_c1 = n_blk * BN + zh * p.b_head_n;
         const int b_c2 = p.b_zdim > 1 ? zb : 0;
-        for (int kb = 0; kb < p.num_kb; kb++, it++) {
+        for (int kb = kb0; kb < kb1; kb++, it++) {
           const int s = it % S;
           bar_wait(&empty[s], ((it / S) & 1) ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -182,7 +186,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
-      for (int kb = 0; kb < p.num_kb; kb++, it++) {
+      const int ks = t % p.ksplit;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; kb++, it++) {
         const int s = it % S;
         bar_wait(&full[s], (it / S) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -191,9 +197,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; k++)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
           umma_commit(&empty[s]);                                   // slot free once these MMAs read it
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);     // accumulator complete
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);          // accumulator complete
         }
         __syncwarp();
       }
@@ -205,7 +211,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int chunks = (BN + 31) / 32;
     int lt = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
-      const int n_blk = t % n_tiles, m_blk = (t / n_tiles) % m_tiles, z = t / (n_tiles * m_tiles);
+      const int ks = t % p.ksplit, tt = t / p.ksplit;
+      const int n_blk = tt % n_tiles, m_blk = (tt / n_tiles) % m_tiles, z = tt / (n_tiles * m_tiles);
       const int zh = z % p.heads, zb = z / p.heads;
       const int acc = lt & 1;
       const int row = m_blk * kBM + q * 32 + lane;
@@ -236,6 +243,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nlim = min(p.N, (n_blk + 1) * BN);  // columns of this tile that exist
         if (!row_ok || n0 >= nlim) continue;
         const bool full32 = n0 + 32 <= nlim;
+        if (p.ksplit > 1) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
+          float* wdst = p.ws + ((size_t)ks * p.M + row) * p.N + n0;
+          if (full32) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              reinterpret_cast<uint4*>(wdst)[u] = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+          } else {
+            for (int j = 0; j < 32; j++) if (n0 + j < nlim) wdst[j] = __uint_as_float(r[j]);
+          }
+          continue;
+        }
         float v[32];
         if (p.bias && full32) {
           __align__(16) __half bb[32];

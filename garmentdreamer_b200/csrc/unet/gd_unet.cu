@@ -387,6 +387,32 @@ __global__ void k_sds_grad(const float* __restrict__ eps, const float* __restric
   grad[i] = w[b] * (np - noise[i]);
 }
 
+// Split-K finalize: y = fp16(alpha * sum_ks ws[ks] + bias + row_bias + residual) (+SiLU).
+__global__ void __launch_bounds__(256)
+k_splitk_finalize(const float* __restrict__ ws, int ksplit, int M, int N, float alpha, const __half* __restrict__ bias,
+                  const __half* __restrict__ row_bias, int rows_per_image, const __half* __restrict__ residual,
+                  __half* __restrict__ C, long long ldc, unsigned flags) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= (long long)M * N) return;
+  const int row = (int)(i / N), n = (int)(i % N);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < ksplit; k++) {
+    const float4 v = *reinterpret_cast<const float4*>(ws + (size_t)k * M * N + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float o[4] = {acc.x * alpha, acc.y * alpha, acc.z * alpha, acc.w * alpha};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (bias) o[j] += __half2float(bias[n + j]);
+    if (row_bias) o[j] += __half2float(row_bias[(long long)(row / rows_per_image) * N + n + j]);
+    if (residual) o[j] += __half2float(residual[(long long)row * ldc + n + j]);
+    if (flags & GD_EPI_SILU) o[j] = silu(o[j]);
+  }
+  __half2* dst = reinterpret_cast<__half2*>(C + (long long)row * ldc + n);
+  dst[0] = __floats2half2_rn(o[0], o[1]);
+  dst[1] = __floats2half2_rn(o[2], o[3]);
+}
+
 // Linear stand-in for the VAE encoder (the VAE is outside this build):
 // latents[b,k,y,x] = sum_c mix[k][c] * mean_{8x8}(2*color[b,c]-1); and its exact transpose.
 __global__ void k_pool_latents(const float* __restrict__ color, const float* __restrict__ mix, float* __restrict__ lat,
@@ -456,8 +482,14 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     // persistent grid of 148 CTAs: trade wave quantisation against tile width (arithmetic intensity)
     const int geglu = (a->flags & GD_EPI_GEGLU) ? 1 : 0;
     const long long mt = ((long long)a->M + gdu::kBM - 1) / gdu::kBM * a->batch;
+    const bool splitk_ok = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) && a->batch == 1 && a->N % 4 == 0 &&
+                           a->c_batch_stride == 0 && a->c_head_stride == 0 && a->K / gdu::kBK >= 24;
     if (a->N <= 64) BN = (a->N + 15) / 16 * 16;
-    else {
+    else if (splitk_ok && mt * ((a->N + 255) / 256) <= 37) {
+      // few output tiles, long K: wide tiles + split-K (below) instead of narrow tiles
+      BN = a->N % 256 == 0 ? 256 : a->N % 160 == 0 ? 160 : 128;
+      if (BN > (a->N + 15) / 16 * 16) BN = (a->N + 15) / 16 * 16;
+    } else {
       const int cands[] = {256, 192, 160, 128, 96, 80, 64};
       double best = -1.0;
       BN = 64;
@@ -517,7 +549,29 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.stages = stages;
   p.m_tiles = (a->M + gdu::kBM - 1) / gdu::kBM;
   p.n_tiles = (a->N + BN - 1) / BN;
-  p.total_tiles = p.m_tiles * p.n_tiles * a->batch;
+  p.ksplit = 1; p.kb_per_split = p.num_kb; p.ws = nullptr;
+  // split-K for under-filled grids with long K (the 8x8 / 16x16 convolutions): partials in fp32,
+  // summed in a fixed order by k_splitk_finalize (deterministic)
+  static float* ws = nullptr;
+  const size_t ws_floats = (size_t)24 << 20;  // 96 MB
+  {
+    const long long tiles = (long long)p.m_tiles * p.n_tiles * a->batch;
+    const bool plain = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) && a->batch == 1 && a->N % 4 == 0 &&
+                       a->c_batch_stride == 0 && a->c_head_stride == 0;
+    if (plain && a->block_n <= 0 && tiles <= 74 && p.num_kb >= 24) {
+      int ks = (int)(148 / tiles);
+      if (ks > p.num_kb / 6) ks = p.num_kb / 6;
+      if (ks > 16) ks = 16;
+      if (ks >= 2 && (size_t)ks * a->M * a->N <= ws_floats) {
+        if (!ws && cudaMalloc(&ws, ws_floats * sizeof(float)) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "gemm: split-K workspace");
+        p.ksplit = ks;
+        p.kb_per_split = (p.num_kb + ks - 1) / ks;
+        p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+        p.ws = ws;
+      }
+    }
+  }
+  p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
   const size_t smem = stages * stage_bytes + 1024 + 256;
   static int num_sms = 0;
   if (!num_sms) {
@@ -530,6 +584,13 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   gdu::k_gemm_tcgen05<<<grid, gdu::kGemmThreads, smem, stream>>>(tmA, tmB, p);
   LAUNCH_CHECK("k_gemm_tcgen05");
+  if (p.ksplit > 1) {
+    const long long n4 = (long long)a->M * a->N / 4;
+    gdu::k_splitk_finalize<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(
+        p.ws, p.ksplit, a->M, a->N, a->alpha, p.bias, p.row_bias, a->rows_per_image > 0 ? a->rows_per_image : 1, p.residual,
+        p.C, p.ldc, p.flags);
+    LAUNCH_CHECK("k_splitk_finalize");
+  }
   return GD_UNET_OK;
 }
 
@@ -560,7 +621,7 @@ int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, 
   p.Tq = Tq; p.Tk = Tk; p.heads = heads; p.n_kv = (Tk + 127) / 128;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.O = reinterpret_cast<__half*>(out); p.ldo = ldo;
-  const size_t smem = gdu::kQBytes + 2 * gdu::kKBytes + 2 * gdu::kVBytes + 2 * gdu::kPBytes + 1024 + 256;
+  const size_t smem = gdu::kQBytes + 2 * gdu::kKBytes + 2 * gdu::kVBytes + 2 * gdu::kPBytes + 1024 + 256 + 1024 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gdu::k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)

@@ -33,7 +33,7 @@ def rnd(*shape, scale=1.0, seed=0):
 
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 16), (256, 320, 320), (1000, 1280, 640), (4096, 320, 2560),
-                                   (77 * 2, 1024, 1280), (64, 1280, 1280), (8192, 2560, 320)])
+                                   (77 * 2, 1024, 1280), (64, 1280, 1280), (8192, 2560, 320), (512, 1280, 5120), (300, 640, 2560)])
 def test_linear(ops, M, K, N):
     x, w, b = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(N)
     y = ops.linear(x, w, b)
@@ -59,7 +59,8 @@ def test_linear_epilogues(ops):
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 320), (3, 16, 16, 1280, 640),
-                                            (2, 8, 8, 1280, 1280), (1, 8, 8, 2560, 1280), (1, 64, 64, 64, 128)])
+                                            (2, 8, 8, 1280, 1280), (1, 8, 8, 2560, 1280), (1, 64, 64, 64, 128),
+                                            (8, 8, 8, 1280, 1280), (8, 8, 8, 2560, 1280)])  # last two: split-K path
 def test_conv3x3(ops, N, H, W, Cin, Cout):
     x = rnd(N, H, W, Cin)
     w = rnd(Cout, 3, 3, Cin, scale=(9 * Cin) ** -0.5)
