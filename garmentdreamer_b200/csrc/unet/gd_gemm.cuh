@@ -38,6 +38,7 @@ struct GemmKParams {
   long long ldc, c_batch_stride, c_head_stride;
   const __half* bias;
   const __half* row_bias;
+  long long row_bias_ld;
   const __half* residual;
   float alpha;
   unsigned flags;
@@ -270,7 +271,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.row_bias) {
-          const __half* rb = p.row_bias + (long long)img * p.N + n0;
+          const __half* rb = p.row_bias + (long long)img * p.row_bias_ld + n0;
           if (full32) {
             __align__(16) __half bb[32];
 #pragma unroll

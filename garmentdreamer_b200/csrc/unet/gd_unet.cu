@@ -64,32 +64,49 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 namespace gdu {
 
 // ---- GroupNorm (+SiLU), NHWC fp16 -------------------------------------------------------------
-// Pass 1: grid (image*group, splits): partial sum / sum-of-squares over a slice of the pixels,
-// written to part[(n*groups+g)*splits + s] (fixed-order merge in pass 2 => deterministic).
+// Pass 1: grid (image, splits): every CTA sweeps ALL channels of its pixel slice with 16-byte
+// loads (thread -> fixed 8-channel chunk(s), strided over pixels), stores per-channel partial sums
+// in shared memory and folds them per group in a fixed order (deterministic) into
+// part[(n*groups+g)*splits + s].
 __global__ void __launch_bounds__(256)
 k_gn_stats(const __half* __restrict__ x, float2* __restrict__ part, int HW, int C, int groups, int splits) {
-  const int n = blockIdx.x / groups, g = blockIdx.x % groups, sp = blockIdx.y;
-  const int cpg = C / groups, cp2 = cpg >> 1;  // cpg is even for every SD layer
+  __shared__ float s_c[2][2560];   // [sum | sumsq][pix_par * C]   (pix_par * C <= 2560)
+  const int n = blockIdx.x, sp = blockIdx.y;
+  const int cpg = C / groups, C8 = C >> 3;
   const int p0 = (int)((long long)HW * sp / splits), p1 = (int)((long long)HW * (sp + 1) / splits);
-  const __half2* xb = reinterpret_cast<const __half2*>(x + (size_t)n * HW * C + (size_t)g * cpg);
-  const int total = (p1 - p0) * cp2;
-  float s = 0.f, ss = 0.f;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int pix = p0 + i / cp2, c = i % cp2;
-    const float2 v = __half22float2(xb[(size_t)pix * (C >> 1) + c]);
-    s += v.x + v.y;
-    ss += v.x * v.x + v.y * v.y;
+  const int pix_par = C8 <= 256 ? 256 / C8 : 1;        // pixels swept in parallel
+  const int iters = C8 <= 256 ? 1 : (C8 + 255) / 256;  // chunks per thread when a pixel is wider than the CTA
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C);
+  for (int it = 0; it < iters; it++) {
+    const int chunk = C8 <= 256 ? (int)(threadIdx.x % C8) : (int)threadIdx.x + 256 * it;
+    const int pl = C8 <= 256 ? (int)(threadIdx.x / C8) : 0;
+    if (pl >= pix_par || chunk >= C8) continue;
+    float s[8], ss[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s[k] = 0.f; ss[k] = 0.f; }
+    for (int pix = p0 + pl; pix < p1; pix += pix_par) {
+      uint4 v = xb[(size_t)pix * C8 + chunk];
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(h[k]);
+        s[2 * k] += f.x; ss[2 * k] += f.x * f.x;
+        s[2 * k + 1] += f.y; ss[2 * k + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      s_c[0][pl * C + chunk * 8 + k] = s[k];
+      s_c[1][pl * C + chunk * 8 + k] = ss[k];
+    }
   }
-  __shared__ float sh[2][8];
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
-  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    s = 0.f; ss = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; w++) { s += sh[0][w]; ss += sh[1][w]; }
-    part[(size_t)blockIdx.x * splits + sp] = make_float2(s, ss);
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int pl = 0; pl < pix_par; pl++)
+      for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += s_c[0][pl * C + c]; b += s_c[1][pl * C + c]; }
+    part[((size_t)n * groups + g) * splits + sp] = make_float2(a, b);
   }
 }
 // Pass 2: grid (image, pixel chunks): per-channel scale/shift table in shared memory, then a
@@ -390,7 +407,7 @@ __global__ void k_sds_grad(const float* __restrict__ eps, const float* __restric
 // Split-K finalize: y = fp16(alpha * sum_ks ws[ks] + bias + row_bias + residual) (+SiLU).
 __global__ void __launch_bounds__(256)
 k_splitk_finalize(const float* __restrict__ ws, int ksplit, int M, int N, float alpha, const __half* __restrict__ bias,
-                  const __half* __restrict__ row_bias, int rows_per_image, const __half* __restrict__ residual,
+                  const __half* __restrict__ row_bias, long long row_bias_ld, int rows_per_image, const __half* __restrict__ residual,
                   __half* __restrict__ C, long long ldc, unsigned flags) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= (long long)M * N) return;
@@ -404,7 +421,7 @@ k_splitk_finalize(const float* __restrict__ ws, int ksplit, int M, int N, float 
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     if (bias) o[j] += __half2float(bias[n + j]);
-    if (row_bias) o[j] += __half2float(row_bias[(long long)(row / rows_per_image) * N + n + j]);
+    if (row_bias) o[j] += __half2float(row_bias[(long long)(row / rows_per_image) * row_bias_ld + n + j]);
     if (residual) o[j] += __half2float(residual[(long long)row * ldc + n + j]);
     if (flags & GD_EPI_SILU) o[j] = silu(o[j]);
   }
@@ -540,6 +557,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.heads = a->heads; p.a_head_k = a->a_head_k; p.a_zflat = a->a_zflat; p.b_head_k = a->b_head_k; p.b_head_n = a->b_head_n; p.b_zdim = a->b_dim[2];
   p.C = reinterpret_cast<__half*>(a->C); p.ldc = a->ldc; p.c_batch_stride = a->c_batch_stride; p.c_head_stride = a->c_head_stride;
   p.bias = reinterpret_cast<const __half*>(a->bias); p.row_bias = reinterpret_cast<const __half*>(a->row_bias);
+  p.row_bias_ld = a->row_bias_ld > 0 ? a->row_bias_ld : a->N;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
@@ -587,7 +605,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   if (p.ksplit > 1) {
     const long long n4 = (long long)a->M * a->N / 4;
     gdu::k_splitk_finalize<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(
-        p.ws, p.ksplit, a->M, a->N, a->alpha, p.bias, p.row_bias, a->rows_per_image > 0 ? a->rows_per_image : 1, p.residual,
+        p.ws, p.ksplit, a->M, a->N, a->alpha, p.bias, p.row_bias, p.row_bias_ld, a->rows_per_image > 0 ? a->rows_per_image : 1, p.residual,
         p.C, p.ldc, p.flags);
     LAUNCH_CHECK("k_splitk_finalize");
   }
@@ -635,13 +653,15 @@ int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, 
 
 int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int N, int HW, int C, int groups,
                       float eps, int silu, gd_ustream_t s) {
-  if (C % groups || (C / groups) % 2 || C % 8 || N * groups > 4096)
+  if (C % groups || (C / groups) % 2 || C % 8 || N * groups > 4096 || groups > 256 || C > 2560)
     return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm: channels per group must be even, C % 8 == 0");
   // partial statistics live in a small static device buffer (N*groups*splits float2 <= 512 KB)
   static float2* part = nullptr;
   if (!part && cudaMalloc(&part, sizeof(float2) * 4096 * 16) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm: cudaMalloc");
-  const int splits = HW >= 4096 ? 16 : HW >= 1024 ? 8 : HW >= 256 ? 4 : 1;
-  gdu::k_gn_stats<<<dim3(N * groups, splits), 256, 0, (cudaStream_t)s>>>((const __half*)x, part, HW, C, groups, splits);
+  int splits = (HW * (C / 8) + 8191) / 8192;  // ~32 sixteen-byte loads per thread
+  if (splits > 16) splits = 16;
+  if (splits < 1) splits = 1;
+  gdu::k_gn_stats<<<dim3(N, splits), 256, 0, (cudaStream_t)s>>>((const __half*)x, part, HW, C, groups, splits);
   LAUNCH_CHECK("k_gn_stats");
   int pix_per_cta = (int)((16384 + C - 1) / C);  // ~16k elements per CTA
   if (pix_per_cta < 1) pix_per_cta = 1;

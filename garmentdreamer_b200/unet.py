@@ -36,6 +36,19 @@ class UNetB200:
         self.w = {}
         for k, v in state_dict.items():
             self.w[k] = self._convert(k, v)
+        # all 22 ResnetBlock2D.time_emb_proj layers as ONE [sum(Cout), 1280] matrix (one launch per forward)
+        names = sorted(k[:-len(".time_emb_proj.weight")] for k in self.w if k.endswith(".time_emb_proj.weight"))
+        self._temb_off, off = {}, 0
+        for nme in names:
+            c = self.w[nme + ".time_emb_proj.weight"].shape[0]
+            self._temb_off[nme] = (off, c)
+            off += c
+        self._temb_w = torch.cat([self.w[nme + ".time_emb_proj.weight"] for nme in names]).contiguous()
+        self._temb_b = torch.cat([self.w[nme + ".time_emb_proj.bias"] for nme in names]).contiguous()
+        # self-attention: to_q and to_k share their input -> one [2C, C] projection
+        for k in [k for k in self.w if k.endswith(".attn1.to_q.weight")]:
+            base = k[:-len(".to_q.weight")]
+            self.w[base + ".to_qk.weight"] = torch.cat([self.w[base + ".to_q.weight"], self.w[base + ".to_k.weight"]]).contiguous()
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = 0
@@ -69,7 +82,8 @@ class UNetB200:
     def _resnet(self, p, x, emb):
         w = self.w
         N, H, W, Cin = x.shape
-        temb = ops.small_linear(emb, w[p + ".time_emb_proj.weight"], w[p + ".time_emb_proj.bias"])  # emb = silu(time emb)
+        off, c = self._temb_off[p]
+        temb = emb[:, off:off + c]   # emb = all time_emb_proj outputs [B, sum(Cout)], row stride sum(Cout)
         h = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=1e-5, silu=True)
         h = ops.conv3x3(h, w[p + ".conv1.weight"], w[p + ".conv1.bias"], row_bias=temb)
         h = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], eps=1e-5, silu=True, out=h)
@@ -83,8 +97,12 @@ class UNetB200:
         w = self.w
         B, T, C = xn.shape
         Tk = ctx.shape[1]
-        q = ops.linear(xn, w[p + ".to_q.weight"])
-        k = ops.linear(ctx, w[p + ".to_k.weight"])
+        if ctx is xn:  # self-attention: fused q|k projection, read through strided views
+            qk = ops.linear(xn, w[p + ".to_qk.weight"])
+            q, k = qk[:, :, :C], qk[:, :, C:]
+        else:
+            q = ops.linear(xn, w[p + ".to_q.weight"])
+            k = ops.linear(ctx, w[p + ".to_k.weight"])
         vt = ops.linear_transposed(ctx, w[p + ".to_v.weight"], (Tk + 7) // 8 * 8)
         o = ops.flash_attention(q, k, vt, heads, Tk, 0.125)  # scores never leave TMEM / smem
         return ops.linear(o, w[p + ".to_out.0.weight"], w[p + ".to_out.0.bias"], residual=resid)
@@ -113,6 +131,7 @@ class UNetB200:
         emb = ops.small_linear(temb, w["time_embedding.linear_1.weight"], w["time_embedding.linear_1.bias"], silu_out=True)
         # every consumer (ResnetBlock2D.time_emb_proj) applies SiLU first: do it once here
         emb = ops.small_linear(emb, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"], silu_out=True)
+        emb = ops.small_linear(emb, self._temb_w, self._temb_b)   # every time_emb_proj at once
         skips = [x]
         for i in range(4):
             for j in range(2):

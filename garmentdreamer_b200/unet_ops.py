@@ -30,6 +30,7 @@ class GdGemmArgs(ctypes.Structure):
         ("ldc", ctypes.c_longlong), ("c_batch_stride", ctypes.c_longlong), ("c_head_stride", ctypes.c_longlong),
         ("bias", ctypes.c_void_p), ("row_bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("alpha", ctypes.c_float), ("flags", ctypes.c_uint), ("block_n", ctypes.c_int),
+        ("row_bias_ld", ctypes.c_longlong),
     ]
 
 
@@ -157,6 +158,8 @@ def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0)
     a.b_stride[:] = [9 * Cin * 2, Cout * 9 * Cin * 2]
     a.C, a.ldc = out.data_ptr(), Cout
     a.bias, a.row_bias, a.residual = _p(bias), _p(row_bias), _p(residual)
+    if row_bias is not None:
+        a.row_bias_ld = row_bias.stride(0)
     a.alpha, a.flags = 1.0, flags
     _gemm(a)
     return out

@@ -68,6 +68,7 @@ typedef struct {
   float alpha;            /* y = alpha * acc (+ bias ...) */
   unsigned flags;
   int block_n;            /* 16..256, multiple of 16; 0 = choose */
+  long long row_bias_ld;  /* row stride of row_bias in elements; 0 = N */
 } GdGemmArgs;
 
 int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
