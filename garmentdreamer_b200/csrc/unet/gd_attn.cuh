@@ -62,6 +62,7 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* o_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
   const int n = p.n_kv, iters = 2 * n;
@@ -89,6 +90,7 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
   const uint32_t tmem_S0 = tmem, tmem_O = tmem + 256;
 
   if (warp == 0) {

@@ -54,6 +54,19 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
   }
   return GD_UNET_OK;
 }
+// Programmatic dependent launch: every kernel of this library triggers its dependents at entry
+// (griddepcontrol.launch_dependents) and waits for its predecessors' memory before touching global
+// data (griddepcontrol.wait), so launch latency and kernel prologues overlap the previous kernel.
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #define LAUNCH_CHECK(what)              \
   do {                                  \
     const int rc_ = check_launch(what); \
@@ -70,6 +83,7 @@ namespace gdu {
 // part[(n*groups+g)*splits + s].
 __global__ void __launch_bounds__(256)
 k_gn_stats(const __half* __restrict__ x, float2* __restrict__ part, int HW, int C, int groups, int splits) {
+  pdl_entry();
   __shared__ float s_c[2][2560];   // [sum | sumsq][pix_par * C]   (pix_par * C <= 2560)
   const int n = blockIdx.x, sp = blockIdx.y;
   const int cpg = C / groups, C8 = C >> 3;
@@ -115,20 +129,25 @@ __global__ void __launch_bounds__(256)
 k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y, const float2* __restrict__ part,
            const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int groups, int splits,
            float eps, int do_silu, int pix_per_cta) {
+  pdl_entry();
   extern __shared__ float2 s_ab[];  // [C] (scale, shift)
+  __shared__ float2 s_mr[256];      // per group (mean, rstd)
   const int n = blockIdx.x, cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  if (threadIdx.x < groups) {
     float s = 0.f, ss = 0.f;
     for (int k = 0; k < splits; k++) {
-      const float2 p = part[((size_t)n * groups + g) * splits + k];
+      const float2 p = part[((size_t)n * groups + threadIdx.x) * splits + k];
       s += p.x; ss += p.y;
     }
     const float inv_n = 1.0f / (float)(HW * cpg);
     const float mean = s * inv_n;
-    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + eps);
-    const float a = rstd * __half2float(gamma[c]);
-    s_ab[c] = make_float2(a, __half2float(beta[c]) - mean * a);
+    s_mr[threadIdx.x] = make_float2(mean, rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2 mr = s_mr[c / cpg];
+    const float a = mr.y * __half2float(gamma[c]);
+    s_ab[c] = make_float2(a, __half2float(beta[c]) - mr.x * a);
   }
   __syncthreads();
   const int C8 = C >> 3;
@@ -155,6 +174,7 @@ k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y, const float2* _
 __global__ void __launch_bounds__(256)
 k_layernorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
             const __half* __restrict__ beta, int rows, int C, float eps) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)row * C);
@@ -178,6 +198,7 @@ k_layernorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* 
 // ---- row softmax in place: one warp per row (cols <= 4096) ---------------------------------
 __global__ void __launch_bounds__(256)
 k_softmax(__half* __restrict__ s, long long rows, int cols, long long ld) {
+  pdl_entry();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -195,6 +216,7 @@ k_softmax(__half* __restrict__ s, long long rows, int cols, long long ld) {
 }
 
 __global__ void k_geglu(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int H) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   const long long r = i / H;
@@ -203,10 +225,12 @@ __global__ void k_geglu(const __half* __restrict__ x, __half* __restrict__ y, lo
   y[i] = __float2half_rn(a * gelu_erf(g));
 }
 __global__ void k_add(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ y, long long n2) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n2) y[i] = __hadd2(a[i], b[i]);
 }
 __global__ void k_upsample2x(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * 2 * H * 2 * W * C8;
   if (i >= total) return;
@@ -218,6 +242,7 @@ __global__ void k_upsample2x(const uint4* __restrict__ x, uint4* __restrict__ y,
   y[i] = x[(((long long)n * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c];
 }
 __global__ void k_space_to_depth(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * H * W * C8;
   if (i >= total) return;
@@ -231,6 +256,7 @@ __global__ void k_space_to_depth(const uint4* __restrict__ x, uint4* __restrict_
 }
 __global__ void k_concat(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long long rows,
                          int Ca8, int Cb8) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int Ct = Ca8 + Cb8;
   if (i >= rows * Ct) return;
@@ -245,6 +271,7 @@ template <int KV>  // KV = 16-byte weight vectors per lane (K = KV * 256)
 __global__ void __launch_bounds__(256)
 k_small_linear(const __half* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ bias,
                __half* __restrict__ y, int Bm, int K, int N, int silu_in, int silu_out) {
+  pdl_entry();
   extern __shared__ __half s_x[];  // [Bm][K]
   for (int i = threadIdx.x; i < Bm * K; i += blockDim.x) {
     float v = __half2float(x[i]);
@@ -294,6 +321,7 @@ k_small_linear(const __half* __restrict__ x, const __half* __restrict__ W, const
   }
 }
 __global__ void k_timestep_embedding(const float* __restrict__ t, __half* __restrict__ y, int Bm, int dim) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim >> 1;
   if (i >= Bm * half) return;
@@ -309,6 +337,7 @@ __global__ void k_timestep_embedding(const float* __restrict__ t, __half* __rest
 __global__ void __launch_bounds__(128)
 k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
           __half* __restrict__ y, int N, int H, int W, int Cout) {
+  pdl_entry();
   extern __shared__ __half s_w[];  // [Cout][36] + [Cout] bias
   for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) s_w[i] = w[i];
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[Cout * 36 + i] = bias[i];
@@ -348,6 +377,7 @@ k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __ha
 __global__ void __launch_bounds__(256)
 k_conv_out(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
            float* __restrict__ y, int N, int H, int W, int Cin) {
+  pdl_entry();
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pix >= (long long)N * H * W) return;
@@ -385,6 +415,7 @@ k_conv_out(const __half* __restrict__ x, const __half* __restrict__ w, const __h
 __global__ void k_add_noise(const float* __restrict__ lat, const float* __restrict__ noise, const float* __restrict__ sa,
                             const float* __restrict__ sb, float* __restrict__ noisy, __half* __restrict__ uin, int B,
                             int reps, int chw) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * chw) return;
   const int b = i / chw;
@@ -395,6 +426,7 @@ __global__ void k_add_noise(const float* __restrict__ lat, const float* __restri
 }
 __global__ void k_sds_grad(const float* __restrict__ eps, const float* __restrict__ noise, const float* __restrict__ w,
                            float s, float* __restrict__ noise_pred, float* __restrict__ grad, int B, int chw) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * chw) return;
   const int b = i / chw;
@@ -409,6 +441,7 @@ __global__ void __launch_bounds__(256)
 k_splitk_finalize(const float* __restrict__ ws, int ksplit, int M, int N, float alpha, const __half* __restrict__ bias,
                   const __half* __restrict__ row_bias, long long row_bias_ld, int rows_per_image, const __half* __restrict__ residual,
                   __half* __restrict__ C, long long ldc, unsigned flags) {
+  pdl_entry();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= (long long)M * N) return;
   const int row = (int)(i / N), n = (int)(i % N);
@@ -434,6 +467,7 @@ k_splitk_finalize(const float* __restrict__ ws, int ksplit, int M, int N, float 
 // latents[b,k,y,x] = sum_c mix[k][c] * mean_{8x8}(2*color[b,c]-1); and its exact transpose.
 __global__ void k_pool_latents(const float* __restrict__ color, const float* __restrict__ mix, float* __restrict__ lat,
                                int B, int H, int W) {
+  pdl_entry();
   const int Ho = H >> 3, Wo = W >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * Ho * Wo) return;
@@ -458,6 +492,7 @@ __global__ void k_pool_latents(const float* __restrict__ color, const float* __r
 // scaled by 1/B like loss_sds (:427).
 __global__ void k_pool_latents_bwd(const float* __restrict__ grad, const float* __restrict__ mix, float* __restrict__ dcolor,
                                    int B, int H, int W, float clip, float scale) {
+  pdl_entry();
   const int Ho = H >> 3, Wo = W >> 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * 3 * H * W) return;
@@ -600,11 +635,11 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
       return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  gdu::k_gemm_tcgen05<<<grid, gdu::kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  launch_pdl(gdu::k_gemm_tcgen05, dim3(grid), dim3(gdu::kGemmThreads), (size_t)(smem), (cudaStream_t)(stream), tmA, tmB, p);
   LAUNCH_CHECK("k_gemm_tcgen05");
   if (p.ksplit > 1) {
     const long long n4 = (long long)a->M * a->N / 4;
-    gdu::k_splitk_finalize<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(
+    launch_pdl(gdu::k_splitk_finalize, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)(stream), 
         p.ws, p.ksplit, a->M, a->N, a->alpha, p.bias, p.row_bias, p.row_bias_ld, a->rows_per_image > 0 ? a->rows_per_image : 1, p.residual,
         p.C, p.ldc, p.flags);
     LAUNCH_CHECK("k_splitk_finalize");
@@ -646,7 +681,7 @@ int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, 
       return fail(GD_UNET_ERR_CUDA, "flash_attn: cannot raise dynamic shared memory limit");
     attr_set = true;
   }
-  gdu::k_flash_attn<<<dim3((Tq + 127) / 128, B * heads), gdu::kAttnThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  launch_pdl(gdu::k_flash_attn, dim3(dim3((Tq + 127) / 128, B * heads)), dim3(gdu::kAttnThreads), (size_t)(smem), (cudaStream_t)(stream), tmQ, tmK, tmV, p);
   LAUNCH_CHECK("k_flash_attn");
   return GD_UNET_OK;
 }
@@ -657,15 +692,16 @@ int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* bet
     return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm: channels per group must be even, C % 8 == 0");
   // partial statistics live in a small static device buffer (N*groups*splits float2 <= 512 KB)
   static float2* part = nullptr;
-  if (!part && cudaMalloc(&part, sizeof(float2) * 4096 * 16) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm: cudaMalloc");
+  if (!part && cudaMalloc(&part, sizeof(float2) * 4096 * 64) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm: cudaMalloc");
   int splits = (HW * (C / 8) + 8191) / 8192;  // ~32 sixteen-byte loads per thread
   if (splits > 16) splits = 16;
   if (splits < 1) splits = 1;
-  gdu::k_gn_stats<<<dim3(N, splits), 256, 0, (cudaStream_t)s>>>((const __half*)x, part, HW, C, groups, splits);
+  while (N * splits < 296 && splits < 64 && HW / (splits * 2) >= 16) splits *= 2;  // at least ~2 CTAs per SM
+  launch_pdl(gdu::k_gn_stats, dim3(dim3(N, splits)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const __half*)x, part, HW, C, groups, splits);
   LAUNCH_CHECK("k_gn_stats");
   int pix_per_cta = (int)((16384 + C - 1) / C);  // ~16k elements per CTA
   if (pix_per_cta < 1) pix_per_cta = 1;
-  gdu::k_gn_apply<<<dim3(N, (HW + pix_per_cta - 1) / pix_per_cta), 256, sizeof(float2) * C, (cudaStream_t)s>>>(
+  launch_pdl(gdu::k_gn_apply, dim3(dim3(N, (HW + pix_per_cta - 1) / pix_per_cta)), dim3(256), (size_t)(sizeof(float2) * C), (cudaStream_t)((cudaStream_t)s), 
       (const __half*)x, (__half*)y, part, (const __half*)gamma, (const __half*)beta, HW, C, groups, splits, eps, silu,
       pix_per_cta);
   LAUNCH_CHECK("k_gn_apply");
@@ -673,45 +709,45 @@ int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* bet
 }
 int gd_unet_layernorm(const void* x, void* y, const void* gamma, const void* beta, int rows, int C, float eps, gd_ustream_t s) {
   if (C % 2) return fail(GD_UNET_ERR_INVALID_ARG, "layernorm: C must be even");
-  gdu::k_layernorm<<<(rows + 7) / 8, 256, 0, (cudaStream_t)s>>>((const __half*)x, (__half*)y, (const __half*)gamma,
+  launch_pdl(gdu::k_layernorm, dim3((rows + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const __half*)x, (__half*)y, (const __half*)gamma,
                                                                (const __half*)beta, rows, C, eps);
   LAUNCH_CHECK("k_layernorm");
   return GD_UNET_OK;
 }
 int gd_unet_softmax(void* sc, long long rows, int cols, long long ld, gd_ustream_t s) {
-  gdu::k_softmax<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)s>>>((__half*)sc, rows, cols, ld);
+  launch_pdl(gdu::k_softmax, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (__half*)sc, rows, cols, ld);
   LAUNCH_CHECK("k_softmax");
   return GD_UNET_OK;
 }
 int gd_unet_geglu(const void* x, void* y, long long rows, int H, gd_ustream_t s) {
-  gdu::k_geglu<<<(unsigned)((rows * H + 255) / 256), 256, 0, (cudaStream_t)s>>>((const __half*)x, (__half*)y, rows, H);
+  launch_pdl(gdu::k_geglu, dim3((unsigned)((rows * H + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const __half*)x, (__half*)y, rows, H);
   LAUNCH_CHECK("k_geglu");
   return GD_UNET_OK;
 }
 int gd_unet_add(const void* a, const void* b, void* y, long long n, gd_ustream_t s) {
   if (n % 2) return fail(GD_UNET_ERR_INVALID_ARG, "add: n must be even");
-  gdu::k_add<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)s>>>((const __half2*)a, (const __half2*)b, (__half2*)y, n / 2);
+  launch_pdl(gdu::k_add, dim3((unsigned)((n / 2 + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const __half2*)a, (const __half2*)b, (__half2*)y, n / 2);
   LAUNCH_CHECK("k_add");
   return GD_UNET_OK;
 }
 int gd_unet_upsample2x(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t s) {
   if (C % 8) return fail(GD_UNET_ERR_INVALID_ARG, "upsample: C % 8");
   const long long total = (long long)N * 4 * H * W * (C / 8);
-  gdu::k_upsample2x<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  launch_pdl(gdu::k_upsample2x, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const uint4*)x, (uint4*)y, N, H, W, C / 8);
   LAUNCH_CHECK("k_upsample2x");
   return GD_UNET_OK;
 }
 int gd_unet_space_to_depth(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t s) {
   if (C % 8 || H % 2 || W % 2) return fail(GD_UNET_ERR_INVALID_ARG, "space_to_depth: C % 8, even H/W");
   const long long total = (long long)N * H * W * (C / 8);
-  gdu::k_space_to_depth<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  launch_pdl(gdu::k_space_to_depth, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const uint4*)x, (uint4*)y, N, H, W, C / 8);
   LAUNCH_CHECK("k_space_to_depth");
   return GD_UNET_OK;
 }
 int gd_unet_concat(const void* a, const void* b, void* y, long long rows, int Ca, int Cb, gd_ustream_t s) {
   if (Ca % 8 || Cb % 8) return fail(GD_UNET_ERR_INVALID_ARG, "concat: C % 8");
   const long long total = rows * ((Ca + Cb) / 8);
-  gdu::k_concat<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>((const uint4*)a, (const uint4*)b, (uint4*)y, rows, Ca / 8, Cb / 8);
+  launch_pdl(gdu::k_concat, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const uint4*)a, (const uint4*)b, (uint4*)y, rows, Ca / 8, Cb / 8);
   LAUNCH_CHECK("k_concat");
   return GD_UNET_OK;
 }
@@ -720,42 +756,42 @@ int gd_unet_small_linear(const void* x, const void* W, const void* bias, void* y
   if (Bm < 1 || Bm > 16 || K % 8 || K > 2048) return fail(GD_UNET_ERR_INVALID_ARG, "small_linear: 1 <= Bm <= 16, K % 8 == 0, K <= 2048");
   const size_t smem = (size_t)Bm * K * 2;
   const dim3 grid((N + 7) / 8);
-#define GD_SL(KV) gdu::k_small_linear<KV><<<grid, 256, smem, (cudaStream_t)s>>>((const __half*)x, (const __half*)W, (const __half*)bias, (__half*)y, Bm, K, N, silu_in, silu_out)
+#define GD_SL(KV) launch_pdl(gdu::k_small_linear<KV>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)((cudaStream_t)s), (const __half*)x, (const __half*)W, (const __half*)bias, (__half*)y, Bm, K, N, silu_in, silu_out)
   if (K <= 512) GD_SL(2); else if (K <= 1280) GD_SL(5); else GD_SL(8);
 #undef GD_SL
   LAUNCH_CHECK("k_small_linear");
   return GD_UNET_OK;
 }
 int gd_unet_timestep_embedding(const float* t, void* y, int Bm, int dim, gd_ustream_t s) {
-  gdu::k_timestep_embedding<<<(Bm * dim / 2 + 127) / 128, 128, 0, (cudaStream_t)s>>>(t, (__half*)y, Bm, dim);
+  launch_pdl(gdu::k_timestep_embedding, dim3((Bm * dim / 2 + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)((cudaStream_t)s), t, (__half*)y, Bm, dim);
   LAUNCH_CHECK("k_timestep_embedding");
   return GD_UNET_OK;
 }
 int gd_unet_conv_in(const void* x, const void* w, const void* bias, void* y, int N, int H, int W, int Cout, gd_ustream_t s) {
   if (Cout % 8 || Cout > 640) return fail(GD_UNET_ERR_INVALID_ARG, "conv_in: Cout % 8, Cout <= 640");
   const long long pix = (long long)N * H * W;
-  gdu::k_conv_in<<<(unsigned)((pix + 127) / 128), 128, (size_t)Cout * 37 * 2, (cudaStream_t)s>>>(
+  launch_pdl(gdu::k_conv_in, dim3((unsigned)((pix + 127) / 128)), dim3(128), (size_t)((size_t)Cout * 37 * 2), (cudaStream_t)((cudaStream_t)s), 
       (const __half*)x, (const __half*)w, (const __half*)bias, (__half*)y, N, H, W, Cout);
   LAUNCH_CHECK("k_conv_in");
   return GD_UNET_OK;
 }
 int gd_unet_conv_out(const void* x, const void* w, const void* bias, float* y, int N, int H, int W, int Cin, gd_ustream_t s) {
   const long long pix = (long long)N * H * W;
-  gdu::k_conv_out<<<(unsigned)((pix + 7) / 8), 256, 0, (cudaStream_t)s>>>((const __half*)x, (const __half*)w,
+  launch_pdl(gdu::k_conv_out, dim3((unsigned)((pix + 7) / 8)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const __half*)x, (const __half*)w,
                                                                          (const __half*)bias, y, N, H, W, Cin);
   LAUNCH_CHECK("k_conv_out");
   return GD_UNET_OK;
 }
 int gd_unet_add_noise(const float* lat, const float* noise, const float* sa, const float* sb, float* noisy, void* uin, int B,
                       int reps, int chw, gd_ustream_t s) {
-  gdu::k_add_noise<<<(B * chw + 255) / 256, 256, 0, (cudaStream_t)s>>>(lat, noise, sa, sb, noisy, (__half*)uin, B, reps, chw);
+  launch_pdl(gdu::k_add_noise, dim3((B * chw + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), lat, noise, sa, sb, noisy, (__half*)uin, B, reps, chw);
   LAUNCH_CHECK("k_add_noise");
   return GD_UNET_OK;
 }
 int gd_unet_pool_latents(const float* color, const float* mix, float* latents, int B, int H, int W, gd_ustream_t s) {
   if (H % 8 || W % 8) return fail(GD_UNET_ERR_INVALID_ARG, "pool_latents: H, W multiples of 8");
   const int n = B * (H / 8) * (W / 8);
-  gdu::k_pool_latents<<<(n + 127) / 128, 128, 0, (cudaStream_t)s>>>(color, mix, latents, B, H, W);
+  launch_pdl(gdu::k_pool_latents, dim3((n + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)((cudaStream_t)s), color, mix, latents, B, H, W);
   LAUNCH_CHECK("k_pool_latents");
   return GD_UNET_OK;
 }
@@ -763,13 +799,13 @@ int gd_unet_pool_latents_bwd(const float* grad, const float* mix, float* dcolor,
                              gd_ustream_t s) {
   if (H % 8 || W % 8) return fail(GD_UNET_ERR_INVALID_ARG, "pool_latents_bwd: H, W multiples of 8");
   const long long n = (long long)B * 3 * H * W;
-  gdu::k_pool_latents_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(grad, mix, dcolor, B, H, W, clip, scale);
+  launch_pdl(gdu::k_pool_latents_bwd, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), grad, mix, dcolor, B, H, W, clip, scale);
   LAUNCH_CHECK("k_pool_latents_bwd");
   return GD_UNET_OK;
 }
 int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float gs, float* np, float* grad, int B, int chw,
                      gd_ustream_t s) {
-  gdu::k_sds_grad<<<(B * chw + 255) / 256, 256, 0, (cudaStream_t)s>>>(eps, noise, w, gs, np, grad, B, chw);
+  launch_pdl(gdu::k_sds_grad, dim3((B * chw + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), eps, noise, w, gs, np, grad, B, chw);
   LAUNCH_CHECK("k_sds_grad");
   return GD_UNET_OK;
 }

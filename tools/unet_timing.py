@@ -11,6 +11,7 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--no-graph", action="store_true")
 ap.add_argument("--torch", action="store_true")
+ap.add_argument("--dump-shapes", default="")
 a = ap.parse_args()
 sd16 = {k: v.cuda().half() for k, v in unet_ref.make_state_dict(0).items()}
 net = UNetB200(sd16, "cuda", use_cuda_graph=not a.no_graph)
@@ -26,6 +27,14 @@ def timeit(fn):
     for _ in range(a.iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / a.iters
+if a.dump_shapes:
+    import json
+    from garmentdreamer_b200 import unet_ops as _ops
+    _rec = []
+    _orig = _ops._gemm
+    def _spy(g):
+        _rec.append([g.M, g.N, g.K, g.batch, g.ntaps, g.flags]); _orig(g)
+    _ops._gemm = _spy
 with torch.no_grad():
     ms = timeit(lambda: net(x, t, encoder_hidden_states=ctx))
     flops = 804.3e9 * a.batch
@@ -33,3 +42,7 @@ with torch.no_grad():
     if a.torch:
         ms = timeit(lambda: unet_ref.unet_forward(sd16, x, t, ctx))
         print(f"torch eager fp16 (SDPA, cuDNN/cuBLAS): {ms:.2f} ms / forward = {flops / ms / 1e9:.1f} TFLOP/s")
+
+if a.dump_shapes:
+    per = len(_rec) // (3 + a.iters)
+    json.dump(_rec[-per:], open(a.dump_shapes, "w"))
