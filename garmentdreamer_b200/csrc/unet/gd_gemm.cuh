@@ -213,9 +213,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue: warps 2..9; quarter q = warp & 3, column half = (warp - 2) >> 2 ----
+    // Per tile a warp owns up to 4 chunks of 32 columns. Everything that does not depend on the
+    // accumulator (bias + time-embedding bias -> per-warp shared memory, residual -> registers) is
+    // fetched BEFORE waiting for the MMA, so the global-load latency hides behind the main loop.
     const int q = warp & 3, half = (warp - 2) >> 2;
     const bool geglu = p.flags & GD_EPI_GEGLU, transposed = p.flags & GD_EPI_TRANSPOSED;
     const int chunks = (BN + 31) / 32;
+    float* sb = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * 128;   // [4 chunks][32] bias sums
+    const bool vec_ok = (p.ldc & 7) == 0 && !geglu && !transposed && p.ksplit == 1;
     int lt = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
       const int ks = t % p.ksplit, tt = t / p.ksplit;
@@ -225,10 +230,37 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;
-      const int img = p.rows_per_image > 0 ? row / p.rows_per_image : 0;
+      const int img = p.rows_per_image > 0 ? (m_blk * kBM + q * 32) / p.rows_per_image : 0;  // uniform per warp
+      const int nlim = min(p.N, (n_blk + 1) * BN);  // columns of this tile that exist
+      // ---- prefetch ----
+      __syncwarp();
+#pragma unroll
+      for (int ci = 0; ci < 4; ci++) {
+        const int n = n_blk * BN + (half + 2 * ci) * 32 + lane;
+        float bsum = 0.f;
+        if (half + 2 * ci < chunks && n < nlim && p.ksplit == 1) {
+          if (p.bias) bsum += __half2float(p.bias[n]);
+          if (p.row_bias) bsum += __half2float(p.row_bias[(long long)img * p.row_bias_ld + n]);
+        }
+        sb[ci * 32 + lane] = bsum;
+      }
+      uint4 rr[4][4];
+#pragma unroll
+      for (int ci = 0; ci < 4; ci++) {
+        const int n0 = n_blk * BN + (half + 2 * ci) * 32;
+        const bool on = p.residual && vec_ok && row_ok && half + 2 * ci < chunks && n0 + 32 <= nlim;
+        const uint4* res = reinterpret_cast<const uint4*>(p.residual + coff + (long long)row * p.ldc + n0);
+#pragma unroll
+        for (int u = 0; u < 4; u++) rr[ci][u] = on ? res[u] : make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      // ---- accumulator ----
       bar_wait(&tmem_full[acc], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = half; c < chunks; c += 2) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ci++) {
+        const int c = half + 2 * ci;
+        if (c >= chunks) break;
         const int c0 = c * 32;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -247,7 +279,6 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
         }
         const int n0 = n_blk * BN + c0;
-        const int nlim = min(p.N, (n_blk + 1) * BN);  // columns of this tile that exist
         if (!row_ok || n0 >= nlim) continue;
         const bool full32 = n0 + 32 <= nlim;
         if (p.ksplit > 1) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
@@ -262,31 +293,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           continue;
         }
         float v[32];
-        if (p.bias && full32) {
-          __align__(16) __half bb[32];
 #pragma unroll
-          for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(bb)[u] = reinterpret_cast<const uint4*>(p.bias + n0)[u];
-#pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) * p.alpha + __half2float(bb[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float x = __uint_as_float(r[j]) * p.alpha;
-            if (p.bias && n0 + j < nlim) x += __half2float(p.bias[n0 + j]);
-            v[j] = x;
-          }
-        }
-        if (p.row_bias) {
-          const __half* rb = p.row_bias + (long long)img * p.row_bias_ld + n0;
-          if (full32) {
-            __align__(16) __half bb[32];
-#pragma unroll
-            for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(bb)[u] = reinterpret_cast<const uint4*>(rb)[u];
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] += __half2float(bb[j]);
-          } else {
-            for (int j = 0; j < 32; j++) if (n0 + j < nlim) v[j] += __half2float(rb[j]);
-          }
+        for (int j4 = 0; j4 < 8; j4++) {
+          const float4 bq = *reinterpret_cast<const float4*>(sb + ci * 32 + j4 * 4);  // broadcast LDS
+          v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) * p.alpha + bq.x;
+          v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) * p.alpha + bq.y;
+          v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * p.alpha + bq.z;
+          v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * p.alpha + bq.w;
         }
         if (geglu) {  // columns come as 16 values followed by their 16 gates
           __half* dst = p.C + coff + (long long)row * p.ldc + (n0 >> 1);
@@ -305,21 +318,19 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {
           __half* dst = p.C + coff + (long long)row * p.ldc + n0;
-          const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
           if (full32 && (p.ldc & 7) == 0) {
             __align__(16) __half o[32];
-            if (res) {
-              __align__(16) __half rr[32];
+            if (p.residual) {
+              const __half* rh = reinterpret_cast<const __half*>(&rr[ci][0]);
 #pragma unroll
-              for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(rr)[u] = reinterpret_cast<const uint4*>(res)[u];
-#pragma unroll
-              for (int j = 0; j < 32; j++) v[j] += __half2float(rr[j]);
+              for (int j = 0; j < 32; j++) v[j] += __half2float(rh[j]);
             }
 #pragma unroll
             for (int j = 0; j < 32; j++) o[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(v[j]) : v[j]);
 #pragma unroll
             for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
           } else {
+            const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
             for (int j = 0; j < 32; j++) {
               if (n0 + j < nlim) {
                 float x = v[j] + (res ? __half2float(res[j]) : 0.0f);

@@ -596,7 +596,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
-  int stages = (int)((200 * 1024) / stage_bytes);   // one persistent CTA per SM owns the shared memory
+  int stages = (int)((196 * 1024) / stage_bytes);   // one persistent CTA per SM owns the shared memory
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -625,7 +625,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     }
   }
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
-  const size_t smem = stages * stage_bytes + 1024 + 256;
+  const size_t smem = stages * stage_bytes + 1024 + 256 + gdu::kEpiWarps * 128 * sizeof(float) + 64;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
