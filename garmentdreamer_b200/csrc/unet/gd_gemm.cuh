@@ -111,6 +111,9 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // TMEM so the epilogue of tile i overlaps the main loop of tile i+1; the TMA ring runs ahead
 // across tile boundaries. 10 warps: 0 = TMA producer, 1 = MMA issuer (+TMEM owner), 2..9 =
 // epilogue (two warps per TMEM lane quarter, each takes half of the tile's 32-column chunks).
+// MODE: 0 plain epilogue (bias / time-embedding / residual / SiLU), 1 GEGLU, 2 transposed store,
+// 3 split-K fp32 partials. One instantiation per mode keeps each kernel's code small (I-cache).
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -217,10 +220,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // accumulator (bias + time-embedding bias -> per-warp shared memory, residual -> registers) is
     // fetched BEFORE waiting for the MMA, so the global-load latency hides behind the main loop.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const bool geglu = p.flags & GD_EPI_GEGLU, transposed = p.flags & GD_EPI_TRANSPOSED;
+    constexpr bool geglu = MODE == 1, transposed = MODE == 2, splitk = MODE == 3;
     const int chunks = (BN + 31) / 32;
     float* sb = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * 128;   // [4 chunks][32] bias sums
-    const bool vec_ok = (p.ldc & 7) == 0 && !geglu && !transposed && p.ksplit == 1;
+    const bool vec_ok = (p.ldc & 7) == 0 && MODE == 0;
     int lt = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
       const int ks = t % p.ksplit, tt = t / p.ksplit;
@@ -238,29 +241,33 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ci = 0; ci < 4; ci++) {
         const int n = n_blk * BN + (half + 2 * ci) * 32 + lane;
         float bsum = 0.f;
-        if (half + 2 * ci < chunks && n < nlim && p.ksplit == 1) {
+        if (half + 2 * ci < chunks && n < nlim && !splitk) {
           if (p.bias) bsum += __half2float(p.bias[n]);
           if (p.row_bias) bsum += __half2float(p.row_bias[(long long)img * p.row_bias_ld + n]);
         }
         sb[ci * 32 + lane] = bsum;
       }
-      uint4 rr[4][4];
-#pragma unroll
-      for (int ci = 0; ci < 4; ci++) {
-        const int n0 = n_blk * BN + (half + 2 * ci) * 32;
-        const bool on = p.residual && vec_ok && row_ok && half + 2 * ci < chunks && n0 + 32 <= nlim;
+      // residual of the warp's first chunk now, of chunk c+2 while chunk c is processed (rolled
+      // loop: unrolling the chunk body 4x made the kernel 258 KB of SASS and thrashed the I-cache)
+      auto fetch_res = [&](int c, uint4 (&dst)[4]) {
+        const int n0 = n_blk * BN + c * 32;
+        const bool on = p.residual && vec_ok && row_ok && c < chunks && n0 + 32 <= nlim;
         const uint4* res = reinterpret_cast<const uint4*>(p.residual + coff + (long long)row * p.ldc + n0);
 #pragma unroll
-        for (int u = 0; u < 4; u++) rr[ci][u] = on ? res[u] : make_uint4(0, 0, 0, 0);
-      }
+        for (int u = 0; u < 4; u++) dst[u] = on ? res[u] : make_uint4(0, 0, 0, 0);
+      };
+      uint4 rnext[4];
+      fetch_res(half, rnext);
       __syncwarp();
       // ---- accumulator ----
       bar_wait(&tmem_full[acc], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = half, ci = 0; c < chunks; c += 2, ci++) {
+        uint4 rcur[4];
 #pragma unroll
-      for (int ci = 0; ci < 4; ci++) {
-        const int c = half + 2 * ci;
-        if (c >= chunks) break;
+        for (int u = 0; u < 4; u++) rcur[u] = rnext[u];
+        fetch_res(c + 2, rnext);
         const int c0 = c * 32;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -281,13 +288,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = n_blk * BN + c0;
         if (!row_ok || n0 >= nlim) continue;
         const bool full32 = n0 + 32 <= nlim;
-        if (p.ksplit > 1) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
+        if constexpr (splitk) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
           float* wdst = p.ws + ((size_t)ks * p.M + row) * p.N + n0;
           if (full32) {
 #pragma unroll
             for (int u = 0; u < 8; u++)
               reinterpret_cast<uint4*>(wdst)[u] = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
           } else {
+#pragma unroll 1
             for (int j = 0; j < 32; j++) if (n0 + j < nlim) wdst[j] = __uint_as_float(r[j]);
           }
           continue;
@@ -301,7 +309,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) * p.alpha + bq.z;
           v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) * p.alpha + bq.w;
         }
-        if (geglu) {  // columns come as 16 values followed by their 16 gates
+        if constexpr (geglu) {  // columns come as 16 values followed by their 16 gates
           __half* dst = p.C + coff + (long long)row * p.ldc + (n0 >> 1);
           __align__(16) __half o[16];
 #pragma unroll
@@ -310,7 +318,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
             reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
           }
-        } else if (transposed) {
+        } else if constexpr (transposed) {
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             const int n = n0 + j;
@@ -321,16 +329,21 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (full32 && (p.ldc & 7) == 0) {
             __align__(16) __half o[32];
             if (p.residual) {
-              const __half* rh = reinterpret_cast<const __half*>(&rr[ci][0]);
+              const __half* rh = reinterpret_cast<const __half*>(&rcur[0]);
 #pragma unroll
               for (int j = 0; j < 32; j++) v[j] += __half2float(rh[j]);
             }
+            if (p.flags & GD_EPI_SILU) {
+#pragma unroll 4
+              for (int j = 0; j < 32; j++) v[j] = silu(v[j]);
+            }
 #pragma unroll
-            for (int j = 0; j < 32; j++) o[j] = __float2half_rn((p.flags & GD_EPI_SILU) ? silu(v[j]) : v[j]);
+            for (int j = 0; j < 32; j++) o[j] = __float2half_rn(v[j]);
 #pragma unroll
             for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
           } else {
             const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
+#pragma unroll 1
             for (int j = 0; j < 32; j++) {
               if (n0 + j < nlim) {
                 float x = v[j] + (res ? __half2float(res[j]) : 0.0f);

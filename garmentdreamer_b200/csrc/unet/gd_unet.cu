@@ -631,11 +631,17 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(gdu::k_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(gdu::k_gemm_tcgen05<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  launch_pdl(gdu::k_gemm_tcgen05, dim3(grid), dim3(gdu::kGemmThreads), (size_t)(smem), (cudaStream_t)(stream), tmA, tmB, p);
+  if (p.ksplit > 1) launch_pdl(gdu::k_gemm_tcgen05<3>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
+  else if (a->flags & GD_EPI_GEGLU) launch_pdl(gdu::k_gemm_tcgen05<1>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
+  else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl(gdu::k_gemm_tcgen05<2>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
+  else launch_pdl(gdu::k_gemm_tcgen05<0>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
   LAUNCH_CHECK("k_gemm_tcgen05");
   if (p.ksplit > 1) {
     const long long n4 = (long long)a->M * a->N / 4;
