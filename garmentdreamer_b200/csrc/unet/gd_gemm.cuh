@@ -32,7 +32,8 @@ struct GemmKParams {
   int M, N, num_kb, kb_per_tap;
   int mode_conv;  // 0: A coords {k, m0, z, 0};  1: conv taps
   int tap_dx[9], tap_dy[9], tap_c[9];
-  int rows_per_image, img_w, rows_box, imgs_box;  // conv tile = imgs_box x rows_box x img_w pixels
+  int rows_per_image, img_w, rows_box, imgs_box;  // conv tile = imgs_box x rows_box x box_w pixels
+  int box_w, tiles_per_row;                       // box_w <= img_w; tiles_per_row = img_w / box_w
   int heads, a_head_k, a_zflat, b_head_k, b_head_n, b_zdim;
   __half* C;
   long long ldc, c_batch_stride, c_head_stride;
@@ -161,11 +162,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         int a_c1, a_c2, a_c3;
         if (p.mode_conv) {
-          const int tile_rows = p.rows_box * p.img_w;
-          const int tiles_per_img = p.rows_per_image / tile_rows;
-          if (p.imgs_box == 1) { a_c3 = m_blk / tiles_per_img; a_c2 = (m_blk % tiles_per_img) * p.rows_box; }
-          else { a_c3 = m_blk * p.imgs_box; a_c2 = 0; }
-          a_c1 = 0;
+          // tile = imgs_box images x rows_box rows x box_w pixels (box_w < img_w: part of one row)
+          const int tiles_per_img = p.rows_per_image / kBM;
+          if (p.imgs_box == 1) {
+            const int t_in = m_blk % tiles_per_img;
+            a_c3 = m_blk / tiles_per_img;
+            a_c2 = (t_in / p.tiles_per_row) * p.rows_box;
+            a_c1 = (t_in % p.tiles_per_row) * p.box_w;
+          } else { a_c3 = m_blk * p.imgs_box; a_c2 = 0; a_c1 = 0; }
         } else {
           a_c1 = m_blk * kBM; a_c2 = p.a_zflat ? z : zb; a_c3 = 0;
         }

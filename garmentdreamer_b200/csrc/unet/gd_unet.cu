@@ -5,6 +5,7 @@
 
 #include "gd_gemm.cuh"
 #include "gd_attn.cuh"
+#include "gd_vae.cuh"
 
 namespace {
 thread_local char g_err[512] = {0};
@@ -98,6 +99,7 @@ k_gn_stats(const __half* __restrict__ x, float2* __restrict__ part, int HW, int 
     float s[8], ss[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { s[k] = 0.f; ss[k] = 0.f; }
+#pragma unroll 4
     for (int pix = p0 + pl; pix < p1; pix += pix_par) {
       uint4 v = xb[(size_t)pix * C8 + chunk];
       const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -584,10 +586,14 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   for (int t = 0; t < 9; t++) { p.tap_dx[t] = a->tap_dx[t]; p.tap_dy[t] = a->tap_dy[t]; p.tap_c[t] = a->tap_c[t]; }
   p.rows_per_image = a->rows_per_image; p.img_w = a->img_w;
   p.rows_box = a->a_box[2]; p.imgs_box = a->a_box[3];
+  p.box_w = a->a_box[1]; p.tiles_per_row = 1;
   if (p.mode_conv) {
-    if (a->a_box[1] != a->img_w || a->rows_per_image != a->img_w * a->img_h || a->img_h % a->a_box[2])
-      return fail(GD_UNET_ERR_INVALID_ARG, "gemm: conv box must span full image rows");
+    if (a->rows_per_image != a->img_w * a->img_h || a->img_h % a->a_box[2] || a->a_box[1] > a->img_w || a->img_w % a->a_box[1])
+      return fail(GD_UNET_ERR_INVALID_ARG, "gemm: conv box must tile the image rows");
+    if (a->a_box[1] < a->img_w && (a->a_box[2] != 1 || a->a_box[3] != 1))
+      return fail(GD_UNET_ERR_INVALID_ARG, "gemm: a box narrower than the image must be one row of one image");
     if (a->a_box[3] > 1 && a->a_box[2] != a->img_h) return fail(GD_UNET_ERR_INVALID_ARG, "gemm: multi-image box must hold whole images");
+    p.tiles_per_row = a->img_w / a->a_box[1];
   }
   p.heads = a->heads; p.a_head_k = a->a_head_k; p.a_zflat = a->a_zflat; p.b_head_k = a->b_head_k; p.b_head_n = a->b_head_n; p.b_zdim = a->b_dim[2];
   p.C = reinterpret_cast<__half*>(a->C); p.ldc = a->ldc; p.c_batch_stride = a->c_batch_stride; p.c_head_stride = a->c_head_stride;
@@ -809,6 +815,123 @@ int gd_unet_pool_latents_bwd(const float* grad, const float* mix, float* dcolor,
   LAUNCH_CHECK("k_pool_latents_bwd");
   return GD_UNET_OK;
 }
+// ---- VAE encoder support (include/gd_unet.h, "VAE" section) -----------------------------------
+namespace {
+float2* gn_part_buffer() {   // partial statistics: up to 8192 (image, group) x 512 splits
+  static float2* part = nullptr;
+  if (!part && cudaMalloc(&part, sizeof(float2) * 8192 * 512) != cudaSuccess) return nullptr;
+  return part;
+}
+int gn_big_splits(int N, int HW, int C) {
+  long long per = 4096;                                    // ~4096 sixteen-byte loads per CTA
+  long long splits = ((long long)HW * (C / 8) + per - 1) / per;
+  if (splits > 512) splits = 512;
+  while (N * splits < 296 && splits < 512 && HW / (splits * 2) >= 16) splits *= 2;
+  if (splits < 1) splits = 1;
+  return (int)splits;
+}
+}  // namespace
+
+int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const void* beta, float* stats, int N, int HW,
+                            int C, int groups, float eps, int silu, gd_ustream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (!stats) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: stats buffer required");
+  if (C % groups || (C / groups) % 2 || C % 8 || N * groups > 8192 || groups > 256 || C > 2560)
+    return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: channels per group must be even, C % 8 == 0, C <= 2560");
+  float2* part = gn_part_buffer();
+  if (!part) return fail(GD_UNET_ERR_CUDA, "groupnorm_stats: cudaMalloc");
+  const int splits = gn_big_splits(N, HW, C);
+  launch_pdl(gdu::k_gn_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, part, HW, C, groups, splits);
+  LAUNCH_CHECK("k_gn_stats");
+  const int total = N * groups;
+  launch_pdl(gdu::k_gn_finalize, dim3((total + 255) / 256), dim3(256), (size_t)0, s, (const float2*)part, (float2*)stats, total,
+             splits, 1.0f / ((float)HW * (float)(C / groups)), eps);
+  LAUNCH_CHECK("k_gn_finalize");
+  if (y) {
+    int pix_per_cta = (32768 + C - 1) / C;
+    const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+    if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
+    launch_pdl(gdu::k_gn_apply_final, dim3(N, (unsigned)chunks), dim3(256), (size_t)(sizeof(float2) * C), s, (const __half*)x,
+               (__half*)y, (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, pix_per_cta);
+    LAUNCH_CHECK("k_gn_apply_final");
+  }
+  return GD_UNET_OK;
+}
+
+int gd_unet_groupnorm_bwd(const void* x, const void* dz, const void* add, void* dx, const void* gamma, const void* beta,
+                          const float* stats, int N, int HW, int C, int groups, int silu, gd_ustream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (C % groups || C % 8 || N * groups > 8192 || groups > 256 || C > 2048)
+    return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: C % groups == 0, C % 8 == 0, C <= 2048");
+  float2* part = gn_part_buffer();
+  if (!part) return fail(GD_UNET_ERR_CUDA, "groupnorm_bwd: cudaMalloc");
+  static float2* bstats = nullptr;
+  if (!bstats && cudaMalloc(&bstats, sizeof(float2) * 8192) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm_bwd: cudaMalloc");
+  const int splits = gn_big_splits(N, HW, C);
+  launch_pdl(gdu::k_gn_bwd_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
+             (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits, silu);
+  LAUNCH_CHECK("k_gn_bwd_stats");
+  const int total = N * groups;
+  launch_pdl(gdu::k_gn_bwd_finalize, dim3((total + 255) / 256), dim3(256), (size_t)0, s, (const float2*)part, bstats, total, splits,
+             1.0f / ((float)HW * (float)(C / groups)));
+  LAUNCH_CHECK("k_gn_bwd_finalize");
+  int pix_per_cta = (32768 + C - 1) / C;
+  const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+  if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: image too large");
+  launch_pdl(gdu::k_gn_bwd_apply, dim3(N, (unsigned)chunks), dim3(256), (size_t)((sizeof(float4) + sizeof(float2)) * C), s, (const __half*)x,
+             (const __half*)dz, (const __half*)add, (__half*)dx, (const float2*)stats, (const float2*)bstats, (const __half*)gamma,
+             (const __half*)beta, HW, C, groups, silu, pix_per_cta);
+  LAUNCH_CHECK("k_gn_bwd_apply");
+  return GD_UNET_OK;
+}
+
+int gd_unet_softmax_bwd(const void* P, void* dP, long long rows, int cols, long long ld, gd_ustream_t s) {
+  if (cols % 8 || ld % 8) return fail(GD_UNET_ERR_INVALID_ARG, "softmax_bwd: cols and ld must be multiples of 8");
+  launch_pdl(gdu::k_softmax_bwd, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)P, (__half*)dP,
+             rows, cols, ld);
+  LAUNCH_CHECK("k_softmax_bwd");
+  return GD_UNET_OK;
+}
+int gd_unet_transpose(const void* x, void* y, int B, int R, int C, gd_ustream_t s) {
+  if (B < 1 || R < 1 || C < 1 || B > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "transpose: bad shape");
+  launch_pdl(gdu::k_transpose, dim3((C + 63) / 64, (R + 63) / 64, B), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)x, (__half*)y, R, C);
+  LAUNCH_CHECK("k_transpose");
+  return GD_UNET_OK;
+}
+int gd_unet_depth_to_space(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t s) {
+  if (C % 8 || H % 2 || W % 2) return fail(GD_UNET_ERR_INVALID_ARG, "depth_to_space: C % 8, even H/W");
+  const long long total = (long long)N * H * W * (C / 8);
+  launch_pdl(gdu::k_depth_to_space, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const uint4*)x, (uint4*)y, N, H, W, C / 8);
+  LAUNCH_CHECK("k_depth_to_space");
+  return GD_UNET_OK;
+}
+int gd_vae_prep(const float* color, void* y, int B, int H, int W, gd_ustream_t s) {
+  const long long n = (long long)B * 4 * H * W;
+  launch_pdl(gdu::k_vae_prep, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, color, (__half*)y, B, (long long)H * W);
+  LAUNCH_CHECK("k_vae_prep");
+  return GD_UNET_OK;
+}
+int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling, gd_ustream_t s) {
+  launch_pdl(gdu::k_vae_sample, dim3((B * 4 * hw + 255) / 256), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)moments, noise, latents, B, hw, scaling);
+  LAUNCH_CHECK("k_vae_sample");
+  return GD_UNET_OK;
+}
+int gd_vae_sample_bwd(const float* grad, const void* moments, const float* noise, void* dmoments, int B, int hw, int Cp,
+                      float scaling, float clip, float gscale, gd_ustream_t s) {
+  if (Cp < 8 || Cp % 8) return fail(GD_UNET_ERR_INVALID_ARG, "vae_sample_bwd: Cp must be a multiple of 8, >= 8");
+  launch_pdl(gdu::k_vae_sample_bwd, dim3((B * hw + 255) / 256), dim3(256), (size_t)0, (cudaStream_t)s, grad, (const __half*)moments, noise,
+             (__half*)dmoments, B, hw, Cp, scaling, clip, gscale);
+  LAUNCH_CHECK("k_vae_sample_bwd");
+  return GD_UNET_OK;
+}
+int gd_vae_dimg(const void* dx, float* dcolor, int B, int H, int W, int Cp, float scale, gd_ustream_t s) {
+  if (Cp < 4 || Cp % 4) return fail(GD_UNET_ERR_INVALID_ARG, "vae_dimg: Cp must be a multiple of 4");
+  const long long n = (long long)B * H * W;
+  launch_pdl(gdu::k_vae_dimg, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)dx, dcolor, B, (long long)H * W, Cp, scale);
+  LAUNCH_CHECK("k_vae_dimg");
+  return GD_UNET_OK;
+}
+
 int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float gs, float* np, float* grad, int B, int chw,
                      gd_ustream_t s) {
   launch_pdl(gdu::k_sds_grad, dim3((B * chw + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), eps, noise, w, gs, np, grad, B, chw);

@@ -1,0 +1,328 @@
+// Kernels around the tcgen05 GEMM for the VAE encoder forward + input-gradient backward
+// (encode_images, Garment_3DGS/threestudio/models/guidance/stable_diffusion_guidance.py:160-167,
+// differentiated by the SDS loss :424-427). All HBM-bound fp16 NHWC sweeps with fp32 math:
+// GroupNorm statistics for tensors of up to 2^20 pixels, GroupNorm(+SiLU) backward, softmax
+// backward, batched transposes, depth-to-space, image pre/post-processing, the diagonal-Gaussian
+// sampler and its backward.
+#pragma once
+#include "gd_gemm.cuh"
+
+namespace gdu {
+
+// ---- GroupNorm statistics, finalised: stats[n*groups+g] = (mean, rstd) -----------------------
+__global__ void __launch_bounds__(256)
+k_gn_finalize(const float2* __restrict__ part, float2* __restrict__ stats, int total, int splits, float inv_n, float eps) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f, ss = 0.f;
+  for (int k = 0; k < splits; k++) {   // fixed order: deterministic
+    const float2 p = part[(size_t)i * splits + k];
+    s += p.x; ss += p.y;
+  }
+  const float mean = s * inv_n;
+  stats[i] = make_float2(mean, rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + eps));
+}
+
+// y = GN(x) (+SiLU) with finalised statistics. grid (image, pixel chunks).
+__global__ void __launch_bounds__(256)
+k_gn_apply_final(const __half* __restrict__ x, __half* __restrict__ y, const float2* __restrict__ stats,
+                 const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int groups,
+                 int do_silu, int pix_per_cta) {
+  pdl_entry();
+  extern __shared__ float2 s_ab[];  // [C] (scale, shift)
+  const int n = blockIdx.x, cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2 mr = stats[(size_t)n * groups + c / cpg];
+    const float a = mr.y * __half2float(gamma[c]);
+    s_ab[c] = make_float2(a, __half2float(beta[c]) - mr.x * a);
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long p0 = (long long)blockIdx.y * pix_per_cta, p1 = min((long long)HW, p0 + pix_per_cta);
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C);
+  uint4* yb = reinterpret_cast<uint4*>(y + (size_t)n * HW * C);
+  for (long long i = p0 * C8 + threadIdx.x; i < p1 * C8; i += blockDim.x) {
+    const int c0 = (int)(i % C8) << 3;
+    uint4 v = xb[i];
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 f = __half22float2(h[k]);
+      const float2 ab0 = s_ab[c0 + 2 * k], ab1 = s_ab[c0 + 2 * k + 1];
+      float a = f.x * ab0.x + ab0.y, b = f.y * ab1.x + ab1.y;
+      if (do_silu) { a = silu(a); b = silu(b); }
+      h[k] = __floats2half2_rn(a, b);
+    }
+    yb[i] = v;
+  }
+}
+
+// ---- GroupNorm (+SiLU) backward --------------------------------------------------------------
+// z = act(GN(x)), upstream dz. With xh = (x - mean) * rstd, y = xh*gamma + beta,
+// g = dz * act'(y):   dx = rstd * (gamma*g - S1 - xh*S2),  S1 = mean_group(gamma*g),
+// S2 = mean_group(gamma*g*xh).
+__device__ __forceinline__ float dsilu(float y) {
+  const float s = 1.0f / (1.0f + __expf(-y));
+  return s * (1.0f + y * (1.0f - s));
+}
+// Pass 1: same sweep as k_gn_stats; per channel sum(g), sum(g*xh) folded with gamma per group.
+__global__ void __launch_bounds__(256)
+k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dz, const float2* __restrict__ stats,
+               const __half* __restrict__ gamma, const __half* __restrict__ beta, float2* __restrict__ part,
+               int HW, int C, int groups, int splits, int do_silu) {
+  pdl_entry();
+  __shared__ float s_c[2][2560];
+  const int n = blockIdx.x, sp = blockIdx.y;
+  const int cpg = C / groups, C8 = C >> 3;
+  const int p0 = (int)((long long)HW * sp / splits), p1 = (int)((long long)HW * (sp + 1) / splits);
+  const int pix_par = C8 <= 256 ? 256 / C8 : 1;
+  const int iters = C8 <= 256 ? 1 : (C8 + 255) / 256;
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C);
+  const uint4* gb = reinterpret_cast<const uint4*>(dz + (size_t)n * HW * C);
+  for (int it = 0; it < iters; it++) {
+    const int chunk = C8 <= 256 ? (int)(threadIdx.x % C8) : (int)threadIdx.x + 256 * it;
+    const int pl = C8 <= 256 ? (int)(threadIdx.x / C8) : 0;
+    if (pl >= pix_par || chunk >= C8) continue;
+    float a[8], b[8], s[8], ss[8];
+    float gam[8], bet[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float2 mr = stats[(size_t)n * groups + (chunk * 8 + k) / cpg];
+      a[k] = mr.y; b[k] = -mr.x * mr.y;            // xh = x*a + b
+      gam[k] = __half2float(gamma[chunk * 8 + k]); bet[k] = __half2float(beta[chunk * 8 + k]);
+      s[k] = 0.f; ss[k] = 0.f;
+    }
+#pragma unroll 2
+    for (int pix = p0 + pl; pix < p1; pix += pix_par) {
+      const uint4 xv = xb[(size_t)pix * C8 + chunk], gv = gb[(size_t)pix * C8 + chunk];
+      const __half2* xh2 = reinterpret_cast<const __half2*>(&xv);
+      const __half2* gh2 = reinterpret_cast<const __half2*>(&gv);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 xf = __half22float2(xh2[k]), gf = __half22float2(gh2[k]);
+        const float xh0 = xf.x * a[2 * k] + b[2 * k], xh1 = xf.y * a[2 * k + 1] + b[2 * k + 1];
+        float g0 = gf.x, g1 = gf.y;
+        if (do_silu) { g0 *= dsilu(xh0 * gam[2 * k] + bet[2 * k]); g1 *= dsilu(xh1 * gam[2 * k + 1] + bet[2 * k + 1]); }
+        s[2 * k] += g0; ss[2 * k] += g0 * xh0;
+        s[2 * k + 1] += g1; ss[2 * k + 1] += g1 * xh1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      s_c[0][pl * C + chunk * 8 + k] = s[k] * gam[k];
+      s_c[1][pl * C + chunk * 8 + k] = ss[k] * gam[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float u = 0.f, v = 0.f;
+    for (int pl = 0; pl < pix_par; pl++)
+      for (int c = g * cpg; c < (g + 1) * cpg; c++) { u += s_c[0][pl * C + c]; v += s_c[1][pl * C + c]; }
+    part[((size_t)n * groups + g) * splits + sp] = make_float2(u, v);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_gn_bwd_finalize(const float2* __restrict__ part, float2* __restrict__ bstats, int total, int splits, float inv_n) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f, ss = 0.f;
+  for (int k = 0; k < splits; k++) {
+    const float2 p = part[(size_t)i * splits + k];
+    s += p.x; ss += p.y;
+  }
+  bstats[i] = make_float2(s * inv_n, ss * inv_n);
+}
+// Pass 2: dx = rstd*(gamma*g - S1 - xh*S2) (+ add).
+__global__ void __launch_bounds__(256)
+k_gn_bwd_apply(const __half* __restrict__ x, const __half* __restrict__ dz, const __half* __restrict__ add,
+               __half* __restrict__ dx, const float2* __restrict__ stats, const float2* __restrict__ bstats,
+               const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int groups,
+               int do_silu, int pix_per_cta) {
+  pdl_entry();
+  extern __shared__ float4 s_p[];   // [C] (a = rstd, b = -mean*rstd, gamma, beta), then float2 [C] (rstd*S1, rstd*S2)
+  float2* s_g = reinterpret_cast<float2*>(s_p + C);
+  const int n = blockIdx.x, cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2 mr = stats[(size_t)n * groups + c / cpg], bs = bstats[(size_t)n * groups + c / cpg];
+    s_p[c] = make_float4(mr.y, -mr.x * mr.y, __half2float(gamma[c]), __half2float(beta[c]));
+    s_g[c] = make_float2(mr.y * bs.x, mr.y * bs.y);
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long p0 = (long long)blockIdx.y * pix_per_cta, p1 = min((long long)HW, p0 + pix_per_cta);
+  const size_t base = (size_t)n * HW * C;
+  const uint4* xb = reinterpret_cast<const uint4*>(x + base);
+  const uint4* gb = reinterpret_cast<const uint4*>(dz + base);
+  const uint4* ab = add ? reinterpret_cast<const uint4*>(add + base) : nullptr;
+  uint4* ob = reinterpret_cast<uint4*>(dx + base);
+  for (long long i = p0 * C8 + threadIdx.x; i < p1 * C8; i += blockDim.x) {
+    const int c0 = (int)(i % C8) << 3;
+    const uint4 xv = xb[i], gv = gb[i];
+    uint4 av = ab ? ab[i] : make_uint4(0, 0, 0, 0);
+    const __half2* xh2 = reinterpret_cast<const __half2*>(&xv);
+    const __half2* gh2 = reinterpret_cast<const __half2*>(&gv);
+    __half2* ah2 = reinterpret_cast<__half2*>(&av);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 xf = __half22float2(xh2[k]), gf = __half22float2(gh2[k]), af = __half22float2(ah2[k]);
+      const float4 q0 = s_p[c0 + 2 * k], q1 = s_p[c0 + 2 * k + 1];
+      const float xh0 = xf.x * q0.x + q0.y, xh1 = xf.y * q1.x + q1.y;
+      float g0 = gf.x, g1 = gf.y;
+      if (do_silu) { g0 *= dsilu(xh0 * q0.z + q0.w); g1 *= dsilu(xh1 * q1.z + q1.w); }
+      const float2 sg0 = s_g[c0 + 2 * k], sg1 = s_g[c0 + 2 * k + 1];
+      const float d0 = q0.x * q0.z * g0 - sg0.x - xh0 * sg0.y + af.x;
+      const float d1 = q1.x * q1.z * g1 - sg1.x - xh1 * sg1.y + af.y;
+      ah2[k] = __floats2half2_rn(d0, d1);
+    }
+    ob[i] = av;
+  }
+}
+
+// ---- softmax backward in place: dS = P * (dP - sum_j P_j dP_j); one warp per row -----------------
+__global__ void __launch_bounds__(256)
+k_softmax_bwd(const __half* __restrict__ P, __half* __restrict__ dP, long long rows, int cols, long long ld) {
+  pdl_entry();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* p4 = reinterpret_cast<const uint4*>(P + row * ld);
+  uint4* d4 = reinterpret_cast<uint4*>(dP + row * ld);
+  const int n8 = cols >> 3;   // cols % 8 == 0 (host-checked)
+  float dot = 0.f;
+  for (int c = lane; c < n8; c += 32) {
+    const uint4 pv = p4[c], dv = d4[c];
+    const __half2* ph = reinterpret_cast<const __half2*>(&pv);
+    const __half2* dh = reinterpret_cast<const __half2*>(&dv);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 a = __half22float2(ph[k]), b = __half22float2(dh[k]);
+      dot += a.x * b.x + a.y * b.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(~0u, dot, o);
+  for (int c = lane; c < n8; c += 32) {
+    const uint4 pv = p4[c];
+    uint4 dv = d4[c];
+    const __half2* ph = reinterpret_cast<const __half2*>(&pv);
+    __half2* dh = reinterpret_cast<__half2*>(&dv);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 a = __half22float2(ph[k]), b = __half22float2(dh[k]);
+      dh[k] = __floats2half2_rn(a.x * (b.x - dot), a.y * (b.y - dot));
+    }
+    d4[c] = dv;
+  }
+}
+
+// ---- batched transpose: x [B, R, C] -> y [B, C, R] (fp16), 64x64 tiles through shared memory ----
+__global__ void __launch_bounds__(256)
+k_transpose(const __half* __restrict__ x, __half* __restrict__ y, int R, int C) {
+  pdl_entry();
+  __shared__ __half t[64][66];
+  const size_t base = (size_t)blockIdx.z * R * C;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 64; j += 8) {
+    const int r = r0 + j, c = c0 + 2 * tx;
+    __half2 v = __floats2half2_rn(0.f, 0.f);
+    if (r < R && c + 1 < C) v = *reinterpret_cast<const __half2*>(x + base + (size_t)r * C + c);
+    else if (r < R && c < C) v = __halves2half2(x[base + (size_t)r * C + c], __float2half_rn(0.f));
+    t[j][2 * tx] = __low2half(v); t[j][2 * tx + 1] = __high2half(v);
+  }
+  __syncthreads();
+  for (int j = ty; j < 64; j += 8) {
+    const int c = c0 + j, r = r0 + 2 * tx;
+    if (c >= C) continue;
+    if (r + 1 < R) *reinterpret_cast<__half2*>(y + base + (size_t)c * R + r) = __halves2half2(t[2 * tx][j], t[2 * tx + 1][j]);
+    else if (r < R) y[base + (size_t)c * R + r] = t[2 * tx][j];
+  }
+}
+
+// ---- depth-to-space (inverse of k_space_to_depth): [N,H/2,W/2,4C] -> [N,H,W,C] ---------------
+__global__ void k_depth_to_space(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C8) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * H * W * C8;
+  if (i >= total) return;
+  const int c = (int)(i % C8);
+  long long p = i / C8;
+  const int ix = (int)(p % W); p /= W;
+  const int iy = (int)(p % H);
+  const int n = (int)(p / H);
+  const int ph = (iy & 1) * 2 + (ix & 1);
+  y[i] = x[((((long long)n * (H >> 1) + (iy >> 1)) * (W >> 1) + (ix >> 1)) * 4 + ph) * C8 + c];
+}
+
+// ---- image pre-processing: color fp32 NCHW [B,3,H,W] in [0,1] -> fp16 NCHW [B,4,H,W] = 2c-1 | 0 ----
+__global__ void k_vae_prep(const float* __restrict__ color, __half* __restrict__ y, int B, long long HW) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * 4 * HW) return;
+  const long long p = i % HW;
+  const int c = (int)((i / HW) % 4), b = (int)(i / (4 * HW));
+  y[i] = __float2half_rn(c < 3 ? 2.0f * color[((long long)b * 3 + c) * HW + p] - 1.0f : 0.0f);
+}
+// ---- DiagonalGaussianDistribution.sample() * scaling: moments fp16 NHWC [B,h,w,8] (mean|logvar) ----
+__global__ void k_vae_sample(const __half* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ lat,
+                             int B, int hw, float scaling) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 4 * hw) return;
+  const int p = i % hw, k = (i / hw) % 4, b = i / (4 * hw);
+  const __half* m = mom + ((size_t)b * hw + p) * 8;
+  const float mean = __half2float(m[k]);
+  const float logvar = fminf(fmaxf(__half2float(m[4 + k]), -30.0f), 20.0f);
+  // the reference samples in fp16: round the sample like posterior.sample() does
+  const float s = __half2float(__float2half_rn(mean + expf(0.5f * logvar) * noise[i]));
+  lat[i] = __half2float(__float2half_rn(s * scaling));
+}
+// Backward of the sampler: grad fp32 NCHW [B,4,h,w] (nan_to_num + clamp(+-clip) applied here,
+// stable_diffusion_guidance.py:418-421) -> d moments fp16 NHWC [B,h,w,Cp] (8 real channels, the
+// rest zero so that the tensor is a valid K operand of the conv-GEMM). `gscale` = loss scale.
+__global__ void k_vae_sample_bwd(const float* __restrict__ grad, const __half* __restrict__ mom,
+                                 const float* __restrict__ noise, __half* __restrict__ dmom, int B, int hw, int Cp,
+                                 float scaling, float clip, float gscale) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * hw) return;
+  const int p = i % hw, b = i / hw;
+  const __half* m = mom + (size_t)i * 8;
+  __half* d = dmom + (size_t)i * Cp;
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const size_t gi = ((size_t)b * 4 + k) * hw + p;
+    float g = grad[gi];
+    if (!(g == g)) g = 0.f;
+    g = fminf(fmaxf(g, -3.4028235e38f), 3.4028235e38f);
+    if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
+    g *= scaling * gscale;
+    const float lv = __half2float(m[4 + k]);
+    const bool inside = lv >= -30.0f && lv <= 20.0f;   // clamp passes gradient inside its range
+    const float std_ = expf(0.5f * fminf(fmaxf(lv, -30.0f), 20.0f));
+    o[k] = __float2half_rn(g);
+    o[4 + k] = __float2half_rn(inside ? g * noise[gi] * 0.5f * std_ : 0.0f);
+  }
+  *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(o);
+  for (int c = 8; c < Cp; c += 8) *reinterpret_cast<uint4*>(d + c) = make_uint4(0, 0, 0, 0);
+}
+// d image: fp16 NHWC [B,H,W,Cp] (3 real channels) -> fp32 NCHW [B,3,H,W] * scale
+// (scale = 2 / loss-scale: d(2c-1)/dc and the unscaling).
+__global__ void k_vae_dimg(const __half* __restrict__ dx, float* __restrict__ dcolor, int B, long long HW, int Cp, float scale) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW) return;
+  const long long p = i % HW;
+  const int b = (int)(i / HW);
+  const uint2 v = *reinterpret_cast<const uint2*>(dx + (size_t)i * Cp);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const float2 a = __half22float2(h[0]), c = __half22float2(h[1]);
+  float* d = dcolor + (size_t)b * 3 * HW + p;
+  d[0] = a.x * scale; d[HW] = a.y * scale; d[2 * HW] = c.x * scale;
+}
+
+}  // namespace gdu

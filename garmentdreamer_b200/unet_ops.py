@@ -68,6 +68,19 @@ def lib():
         L.gd_unet_sds_grad.argtypes = [vp, vp, vp, f, vp, vp, i, i, vp]
         L.gd_unet_pool_latents.argtypes = [vp, vp, vp, i, i, i, vp]
         L.gd_unet_pool_latents_bwd.argtypes = [vp, vp, vp, i, i, i, f, f, vp]
+        L.gd_unet_groupnorm_stats.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, f, i, vp]
+        L.gd_unet_groupnorm_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+        L.gd_unet_softmax_bwd.argtypes = [vp, vp, ll, i, ll, vp]
+        L.gd_unet_transpose.argtypes = [vp, vp, i, i, i, vp]
+        L.gd_unet_depth_to_space.argtypes = [vp, vp, i, i, i, i, vp]
+        L.gd_vae_prep.argtypes = [vp, vp, i, i, i, vp]
+        L.gd_vae_sample.argtypes = [vp, vp, vp, i, i, f, vp]
+        L.gd_vae_sample_bwd.argtypes = [vp, vp, vp, vp, i, i, i, f, f, f, vp]
+        L.gd_vae_dimg.argtypes = [vp, vp, i, i, i, i, f, vp]
+        for name in ("groupnorm_stats", "groupnorm_bwd", "softmax_bwd", "transpose", "depth_to_space"):
+            getattr(L, "gd_unet_" + name).restype = ctypes.c_int
+        for name in ("prep", "sample", "sample_bwd", "dimg"):
+            getattr(L, "gd_vae_" + name).restype = ctypes.c_int
         for name in ("gemm", "flash_attn", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
                      "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad",
                      "pool_latents", "pool_latents_bwd"):
@@ -115,15 +128,42 @@ def linear(x, w, bias=None, *, residual=None, out=None, flags=0, alpha=1.0, bloc
     a.B = w.data_ptr()
     a.b_dim[:] = [K, N, 1]
     a.b_stride[:] = [K * 2, N * K * 2]
-    a.C, a.ldc = out.data_ptr(), n_out
+    a.C, a.ldc = out.data_ptr(), (out.stride(-2) if out.dim() >= 2 else n_out)
     a.bias, a.residual = _p(bias), _p(residual)
     a.alpha, a.flags, a.block_n = alpha, flags, block_n
     _gemm(a)
     return out
 
 
+def bmm_nt(x, y, *, alpha=1.0, out=None):
+    """Batched C[b] = alpha * x[b] @ y[b]^T ; x [B,M,K], y [B,N,K] (K contiguous) -> [B,M,N]."""
+    _h(x); _h(y)
+    B, M, K = x.shape
+    N = y.shape[1]
+    if out is None:
+        out = torch.empty((B, M, N), dtype=torch.float16, device=x.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = M, N, K, B, 1
+    a.A = x.data_ptr()
+    a.a_dim[:] = [K, M, B, 1]
+    a.a_stride[:] = [K * 2, M * K * 2, B * M * K * 2]
+    a.a_box[:] = [64, 128, 1, 1]
+    a.B = y.data_ptr()
+    a.b_dim[:] = [K, N, B]
+    a.b_stride[:] = [K * 2, N * K * 2]
+    a.C, a.ldc = out.data_ptr(), N
+    a.c_batch_stride = M * N
+    a.alpha = alpha
+    _gemm(a)
+    return out
+
+
 def _conv_box(H, W, N):
-    if W > 128 or 128 % W:
+    if W >= 128:   # tile = 128 pixels of one image row
+        if W % 128:
+            raise ValueError(f"conv width {W} must be a multiple of 128")
+        return 128, 1, 1
+    if 128 % W:
         raise ValueError(f"conv width {W} must divide 128")
     rows = 128 // W
     if rows <= H:
@@ -135,34 +175,45 @@ def _conv_box(H, W, N):
     return W, H, rows // H
 
 
-def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0):
-    """3x3, stride 1, pad 1 over NHWC x[N,H,W,Cin]; w[Cout,3,3,Cin]."""
+def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0):
+    """Implicit-GEMM convolution over NHWC x[N,H,W,Cx]: out[n,y,x,:] = sum_t x[n, y+dy_t, x+dx_t,
+    c_t : c_t+Ck] @ w[:, t*Ck:(t+1)*Ck]^T (zero outside the image). taps = [(dx, dy, c)], w
+    [Cout, len(taps)*Ck]. `out` may be a channel slice of a wider NHWC tensor."""
     _h(x); _h(w)
-    N, H, W, Cin = x.shape
+    N, H, W, Cx = x.shape
     Cout = w.shape[0]
+    nt = len(taps)
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=torch.float16, device=x.device)
     a = GdGemmArgs()
-    a.M, a.N, a.K, a.batch, a.heads = N * H * W, Cout, 9 * Cin, 1, 1
+    a.M, a.N, a.K, a.batch, a.heads = N * H * W, Cout, nt * Ck, 1, 1
     a.A = x.data_ptr()
-    a.a_dim[:] = [Cin, W, H, N]
-    a.a_stride[:] = [Cin * 2, W * Cin * 2, H * W * Cin * 2]
+    a.a_dim[:] = [Cx, W, H, N]
+    a.a_stride[:] = [Cx * 2, W * Cx * 2, H * W * Cx * 2]
     bw, bh, bn = _conv_box(H, W, N)
     a.a_box[:] = [64, bw, bh, bn]
-    a.ntaps, a.Ck = 9, Cin
-    for t in range(9):
-        a.tap_dx[t], a.tap_dy[t], a.tap_c[t] = t % 3 - 1, t // 3 - 1, 0
+    a.ntaps, a.Ck = nt, Ck
+    for t, (dx, dy, c) in enumerate(taps):
+        a.tap_dx[t], a.tap_dy[t], a.tap_c[t] = dx, dy, c
     a.rows_per_image, a.img_w, a.img_h = H * W, W, H
     a.B = w.data_ptr()
-    a.b_dim[:] = [9 * Cin, Cout, 1]
-    a.b_stride[:] = [9 * Cin * 2, Cout * 9 * Cin * 2]
-    a.C, a.ldc = out.data_ptr(), Cout
+    a.b_dim[:] = [nt * Ck, Cout, 1]
+    a.b_stride[:] = [nt * Ck * 2, Cout * nt * Ck * 2]
+    a.C, a.ldc = out.data_ptr(), out.stride(2)
     a.bias, a.row_bias, a.residual = _p(bias), _p(row_bias), _p(residual)
     if row_bias is not None:
         a.row_bias_ld = row_bias.stride(0)
     a.alpha, a.flags = 1.0, flags
     _gemm(a)
     return out
+
+
+_TAPS_3X3 = [(t % 3 - 1, t // 3 - 1, 0) for t in range(9)]
+
+
+def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0):
+    """3x3, stride 1, pad 1 over NHWC x[N,H,W,Cin]; w[Cout,3,3,Cin]."""
+    return conv_taps(x, w, _TAPS_3X3, x.shape[-1], bias, row_bias=row_bias, residual=residual, out=out, flags=flags)
 
 
 def conv3x3_stride2(x, w, bias=None, *, s2d=None, out=None):
@@ -266,7 +317,7 @@ def flash_attention(q, k, vt, heads, Tk, scale=0.125, out=None):
     return out
 
 
-def linear_transposed(x, w, Tk_pad, out=None):
+def linear_transposed(x, w, Tk_pad, out=None, bias=None):
     """V^T projection: x [B,T,K] @ w[N,K]^T stored transposed per batch -> [B,N,Tk_pad]."""
     _h(x); _h(w)
     B, T, K = x.shape
@@ -284,6 +335,7 @@ def linear_transposed(x, w, Tk_pad, out=None):
     a.b_stride[:] = [K * 2, N * K * 2]
     a.C, a.ldc = out.data_ptr(), Tk_pad
     a.c_batch_stride = N * Tk_pad
+    a.bias = _p(bias)
     a.alpha, a.flags = 1.0, EPI_TRANSPOSED
     _gemm(a)
     return out
@@ -369,4 +421,56 @@ def conv_out(x, w, bias):
     out = torch.empty((N, 4, H, W), dtype=torch.float32, device=x.device)
     _chk(lib().gd_unet_conv_out(_h(x).data_ptr(), _h(w).data_ptr(), bias.data_ptr(), out.data_ptr(), N, H, W, Cin,
                                 _stream()), "conv_out")
+    return out
+
+
+# ---- VAE encoder support (include/gd_unet.h, "VAE" section) ---------------------------------
+def groupnorm_stats(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, apply=True):
+    """GroupNorm(+SiLU) that also returns the (mean, rstd) table [N*groups, 2] fp32 for the backward."""
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    stats = torch.empty((N * groups, 2), dtype=torch.float32, device=x.device)
+    if apply and out is None:
+        out = torch.empty_like(x)
+    _chk(lib().gd_unet_groupnorm_stats(_h(x).data_ptr(), out.data_ptr() if apply else None, gamma.data_ptr(), beta.data_ptr(),
+                                       stats.data_ptr(), N, HW, C, groups, eps, int(silu), _stream()), "groupnorm_stats")
+    return out, stats
+
+
+def groupnorm_bwd(x, dz, gamma, beta, stats, groups=32, silu=False, add=None, out=None):
+    """dx of z = act(GN(x)) given dz (+ add)."""
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    out = torch.empty_like(x) if out is None else out
+    _chk(lib().gd_unet_groupnorm_bwd(_h(x).data_ptr(), _h(dz).data_ptr(), _p(add), out.data_ptr(), gamma.data_ptr(),
+                                     beta.data_ptr(), stats.data_ptr(), N, HW, C, groups, int(silu), _stream()), "groupnorm_bwd")
+    return out
+
+
+def softmax_bwd_(p, dp):
+    ld = p.shape[-1]
+    _chk(lib().gd_unet_softmax_bwd(_h(p).data_ptr(), _h(dp).data_ptr(), p.numel() // ld, ld, ld, _stream()), "softmax_bwd")
+    return dp
+
+
+def transpose(x, out=None):
+    """[B,R,C] -> [B,C,R]"""
+    B, R, C = x.shape
+    out = torch.empty((B, C, R), dtype=torch.float16, device=x.device) if out is None else out
+    _chk(lib().gd_unet_transpose(_h(x).data_ptr(), out.data_ptr(), B, R, C, _stream()), "transpose")
+    return out
+
+
+def space_to_depth(x, out=None):
+    N, H, W, C = x.shape
+    out = torch.empty((N, H // 2, W // 2, 4 * C), dtype=torch.float16, device=x.device) if out is None else out
+    _chk(lib().gd_unet_space_to_depth(_h(x).data_ptr(), out.data_ptr(), N, H, W, C, _stream()), "space_to_depth")
+    return out
+
+
+def depth_to_space(x, out=None):
+    N, Ho, Wo, C4 = x.shape
+    C = C4 // 4
+    out = torch.empty((N, 2 * Ho, 2 * Wo, C), dtype=torch.float16, device=x.device) if out is None else out
+    _chk(lib().gd_unet_depth_to_space(_h(x).data_ptr(), out.data_ptr(), N, 2 * Ho, 2 * Wo, C, _stream()), "depth_to_space")
     return out

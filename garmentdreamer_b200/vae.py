@@ -1,0 +1,225 @@
+"""B200-native SD-2.1 VAE encoder: forward AND input-gradient backward (fp16, channels-last).
+
+Replaces ``StableDiffusionGuidance.encode_images`` of the reference
+(Garment_3DGS/threestudio/models/guidance/stable_diffusion_guidance.py:160-167)
+
+    imgs = imgs * 2 - 1
+    latents = vae.encode(imgs.half()).latent_dist.sample() * vae.config.scaling_factor
+
+together with the autograd backward the SDS loss drives through it (:424-427): the only trainable
+quantity upstream is the rendered image, so the backward is data-gradient only (frozen weights,
+`p.requires_grad_(False)` at :99-102). The reference executes diffusers 0.19.0 AutoencoderKL
+(not in the reference tree; module tree restated in oracle/vae_ref.py).
+
+Every convolution / Linear / attention matmul, forward and backward, is the tcgen05 implicit-GEMM
+kernel of libgd_unet.so (dgrad = the same kernel with flipped, transposed weights prepared once);
+GroupNorm(+SiLU) forward/backward, softmax backward, transposes and the sampler are fused sweeps
+(csrc/unet/gd_vae.cuh). No torch math on the path; Python only orders the calls.
+"""
+import torch
+
+from . import unet_ops as ops
+
+CH = (128, 256, 512, 512)
+SCALING = 0.18215
+EPS = 1e-6
+GRAD_SCALE = 256.0   # loss scale for the fp16 backward (power of two: exact; removed in gd_vae_dimg)
+
+# stride-2 3x3 conv with padding (0,1,0,1) on the space-to-depth tensor: tap (ky,kx) reads phase
+# (ky&1, kx&1) at shift (ky>>1, kx>>1)
+_DOWN_TAPS = [((kx >> 1), (ky >> 1), ((ky & 1) * 2 + (kx & 1))) for ky in range(3) for kx in range(3)]
+
+
+class VAEEncoderB200:
+    """encode(imgs01, noise) -> latents; backward(grad_latents) -> d imgs01 (both fp32 NCHW)."""
+
+    def __init__(self, state_dict, device="cuda"):
+        self.device = torch.device(device)
+        ops.lib()  # fail loudly if the CUDA library is missing
+        sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()}
+        self.w = {}
+        h = lambda t: t.to(torch.float16).contiguous()
+        for k, v in sd.items():
+            if v.dim() == 1:
+                self.w[k] = h(v)
+        # conv_in: [128,3,3,3] -> [128,3,3,4] (4th input channel is zero padding)
+        w = sd["encoder.conv_in.weight"]
+        w4 = torch.zeros(w.shape[0], 3, 3, 4, device=self.device)
+        w4[..., :3] = w.permute(0, 2, 3, 1)
+        self.w["conv_in.fwd"] = h(w4)
+        wt = torch.zeros(16, 3, 3, w.shape[0], device=self.device)          # dgrad: 3 real outputs of 16
+        wt[:3] = w.flip(2, 3).permute(1, 2, 3, 0)
+        self.w["conv_in.bwd"] = h(wt.reshape(16, -1))
+        for k in [k for k in sd if k.endswith(".weight") and sd[k].dim() == 4 and k != "encoder.conv_in.weight"]:
+            base, v = k[:-len(".weight")], sd[k]
+            if base in ("encoder.conv_out", "quant_conv"):
+                continue
+            if v.shape[2] == 1:      # conv_shortcut 1x1 -> Linear (+ its transpose for the backward)
+                m = v.reshape(v.shape[0], v.shape[1])
+                self.w[base + ".fwd"], self.w[base + ".bwd"] = h(m), h(m.t())
+            elif "downsamplers" in base:
+                self.w[base + ".fwd"] = h(v.permute(0, 2, 3, 1).reshape(v.shape[0], -1))   # [Cout, (ky,kx,Cin)]
+                # dgrad w.r.t. the space-to-depth tensor, one GEMM per phase: taps with that phase
+                for ph in range(4):
+                    taps = [(ky, kx) for ky in range(3) for kx in range(3) if (ky & 1) * 2 + (kx & 1) == ph]
+                    m = torch.stack([v[:, :, ky, kx].t() for ky, kx in taps], 1)            # [Cin, ntaps, Cout]
+                    self.w[f"{base}.bwd{ph}"] = h(m.reshape(v.shape[1], -1))
+            else:
+                self.w[base + ".fwd"] = h(v.permute(0, 2, 3, 1).reshape(v.shape[0], -1))
+                self.w[base + ".bwd"] = h(v.flip(2, 3).permute(1, 2, 3, 0).reshape(v.shape[1], -1))
+        # conv_out (512 -> 8) and quant_conv (1x1, 8 -> 8) are both linear: folded into one conv
+        wq = sd["quant_conv.weight"].reshape(8, 8)
+        wo = torch.einsum("ab,bcyx->acyx", wq, sd["encoder.conv_out.weight"])
+        self.w["conv_out.fwd"] = h(wo.permute(0, 2, 3, 1).reshape(8, -1))
+        self.w["conv_out.bias"] = h(wq @ sd["encoder.conv_out.bias"] + sd["quant_conv.bias"])
+        wt = torch.zeros(512, 3, 3, 64, device=self.device)                 # dgrad: 8 real input channels of 64
+        wt[..., :8] = wo.flip(2, 3).permute(1, 2, 3, 0)
+        self.w["conv_out.bwd"] = h(wt.reshape(512, -1))
+        a = "encoder.mid_block.attentions.0"
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            m = sd[f"{a}.{n}.weight"]
+            self.w[f"{a}.{n}.fwd"], self.w[f"{a}.{n}.bwd"] = h(m), h(m.t())
+        self._saved = None
+
+    # ---- module-like surface ---------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(self.w.values())
+
+    def requires_grad_(self, flag=False):
+        return self
+
+    # ---- blocks ----------------------------------------------------------------------------
+    def _resnet_fwd(self, p, x, saved):
+        w = self.w
+        n1, st1 = ops.groupnorm_stats(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=EPS, silu=True)
+        h1 = ops.conv3x3(n1, w[p + ".conv1.fwd"], w[p + ".conv1.bias"])
+        n2, st2 = ops.groupnorm_stats(h1, w[p + ".norm2.weight"], w[p + ".norm2.bias"], eps=EPS, silu=True, out=n1 if n1.shape == h1.shape else None)
+        sc = x
+        if p + ".conv_shortcut.fwd" in w:
+            N, H, W, C = x.shape
+            sc = ops.linear(x.view(N * H * W, C), w[p + ".conv_shortcut.fwd"], w[p + ".conv_shortcut.bias"]).view(N, H, W, -1)
+        out = ops.conv3x3(n2, w[p + ".conv2.fwd"], w[p + ".conv2.bias"], residual=sc)
+        saved.append(("resnet", p, x, st1, h1, st2))
+        return out
+
+    def _resnet_bwd(self, rec, dout):
+        _, p, x, st1, h1, st2 = rec
+        w = self.w
+        dn2 = ops.conv3x3(dout, w[p + ".conv2.bwd"])
+        dh1 = ops.groupnorm_bwd(h1, dn2, w[p + ".norm2.weight"], w[p + ".norm2.bias"], st2, silu=True, out=dn2)
+        dn1 = ops.conv3x3(dh1, w[p + ".conv1.bwd"])
+        add = dout
+        if p + ".conv_shortcut.bwd" in w:
+            N, H, W, C = dout.shape
+            add = ops.linear(dout.view(N * H * W, C), w[p + ".conv_shortcut.bwd"]).view(N, H, W, -1)
+        return ops.groupnorm_bwd(x, dn1, w[p + ".norm1.weight"], w[p + ".norm1.bias"], st1, silu=True, add=add, out=dn1)
+
+    def _down_fwd(self, p, x, saved):
+        s2d = ops.space_to_depth(x)
+        C = x.shape[-1]
+        taps = [(dx, dy, ph * C) for dx, dy, ph in _DOWN_TAPS]
+        saved.append(("down", p, C))
+        return ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"])
+
+    def _down_bwd(self, rec, dout):
+        _, p, C = rec
+        N, Ho, Wo, Cout = dout.shape
+        ds2d = torch.empty((N, Ho, Wo, 4 * C), dtype=torch.float16, device=dout.device)
+        for ph in range(4):
+            taps = [(-(kx >> 1), -(ky >> 1), 0) for ky in range(3) for kx in range(3) if (ky & 1) * 2 + (kx & 1) == ph]
+            ops.conv_taps(dout, self.w[f"{p}.bwd{ph}"], taps, Cout, out=ds2d[..., ph * C:(ph + 1) * C])
+        return ops.depth_to_space(ds2d)
+
+    def _attn_fwd(self, p, x, saved):
+        w = self.w
+        N, H, W, C = x.shape
+        T = H * W
+        hn, st = ops.groupnorm_stats(x, w[p + ".group_norm.weight"], w[p + ".group_norm.bias"], eps=EPS, silu=False)
+        hn = hn.view(N, T, C)
+        q = ops.linear(hn, w[p + ".to_q.fwd"], w[p + ".to_q.bias"])
+        k = ops.linear(hn, w[p + ".to_k.fwd"], w[p + ".to_k.bias"])
+        v = ops.linear(hn, w[p + ".to_v.fwd"], w[p + ".to_v.bias"])
+        scale = float(C) ** -0.5
+        P = ops.softmax_(ops.bmm_nt(q, k, alpha=scale), T)     # [N,T,T]; one head of 512
+        o = ops.bmm_nt(P, ops.transpose(v))                    # P @ v
+        out = ops.linear(o, w[p + ".to_out.0.fwd"], w[p + ".to_out.0.bias"], residual=x.view(N, T, C)).view(N, H, W, C)
+        saved.append(("attn", p, x, st, q, k, v, P, scale))
+        return out
+
+    def _attn_bwd(self, rec, dout):
+        _, p, x, st, q, k, v, P, scale = rec
+        w = self.w
+        N, H, W, C = x.shape
+        T = H * W
+        do = ops.linear(dout.view(N, T, C), w[p + ".to_out.0.bwd"])
+        dv = ops.bmm_nt(ops.transpose(P), ops.transpose(do))                   # P^T do
+        dS = ops.softmax_bwd_(P, ops.bmm_nt(do, v))                            # dP = do v^T, then softmax bwd in place
+        dq = ops.bmm_nt(dS, ops.transpose(k), alpha=scale)                     # dS k
+        dk = ops.bmm_nt(ops.transpose(dS), ops.transpose(q), alpha=scale)      # dS^T q
+        dhn = ops.linear(dq, w[p + ".to_q.bwd"])
+        dhn = ops.linear(dk, w[p + ".to_k.bwd"], residual=dhn, out=dhn)
+        dhn = ops.linear(dv, w[p + ".to_v.bwd"], residual=dhn, out=dhn)
+        return ops.groupnorm_bwd(x, dhn.view(N, H, W, C), w[p + ".group_norm.weight"], w[p + ".group_norm.bias"], st,
+                                 silu=False, add=dout)
+
+    # ---- forward / backward ------------------------------------------------------------------
+    def encode(self, imgs01, noise, keep_for_backward=True):
+        """imgs01 fp32 [B,3,H,W] in [0,1] (H, W multiples of 128); noise fp32 [B,4,H/8,W/8] replaces
+        the sampler's randn. Returns latents fp32 [B,4,H/8,W/8]."""
+        if not imgs01.is_cuda:
+            raise RuntimeError("garmentdreamer_b200 VAE is CUDA-only (no CPU fallback)")
+        L, st = ops.lib(), ops._stream()
+        B, _, H, W = imgs01.shape
+        if H % 128 or W % 128:
+            raise ValueError("VAE encoder: image height / width must be multiples of 128")
+        imgs01 = imgs01.detach().float().contiguous()
+        noise = noise.detach().float().contiguous()
+        x4 = torch.empty((B, 4, H, W), dtype=torch.float16, device=imgs01.device)
+        ops._chk(L.gd_vae_prep(imgs01.data_ptr(), x4.data_ptr(), B, H, W, st), "vae_prep")
+        saved = []
+        x = ops.conv_in(x4, self.w["conv_in.fwd"], self.w["encoder.conv_in.bias"])
+        for i in range(4):
+            for j in range(2):
+                x = self._resnet_fwd(f"encoder.down_blocks.{i}.resnets.{j}", x, saved)
+            if i < 3:
+                x = self._down_fwd(f"encoder.down_blocks.{i}.downsamplers.0.conv", x, saved)
+        x = self._resnet_fwd("encoder.mid_block.resnets.0", x, saved)
+        x = self._attn_fwd("encoder.mid_block.attentions.0", x, saved)
+        x = self._resnet_fwd("encoder.mid_block.resnets.1", x, saved)
+        n, stn = ops.groupnorm_stats(x, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"], eps=EPS, silu=True)
+        mom = ops.conv3x3(n, self.w["conv_out.fwd"], self.w["conv_out.bias"])     # [B,h,w,8] = mean | logvar
+        h, w_ = H // 8, W // 8
+        lat = torch.empty((B, 4, h, w_), dtype=torch.float32, device=imgs01.device)
+        ops._chk(L.gd_vae_sample(mom.data_ptr(), noise.data_ptr(), lat.data_ptr(), B, h * w_, SCALING, st), "vae_sample")
+        self._saved = (saved, x, stn, mom, noise, (B, H, W)) if keep_for_backward else None
+        return lat
+
+    def backward(self, grad_latents, clip=0.0, scale=1.0):
+        """d<latents, g>/d imgs01 for g = nan_to_num(clamp(grad_latents, +-clip)) * scale
+        (stable_diffusion_guidance.py:418-427). fp32 [B,3,H,W]."""
+        if self._saved is None:
+            raise RuntimeError("VAEEncoderB200.backward() needs a preceding encode(keep_for_backward=True)")
+        saved, x_out, stn, mom, noise, (B, H, W) = self._saved
+        self._saved = None
+        L, st = ops.lib(), ops._stream()
+        h, w_ = H // 8, W // 8
+        g = grad_latents.detach().float().contiguous()
+        dmom = torch.empty((B, h, w_, 64), dtype=torch.float16, device=g.device)
+        ops._chk(L.gd_vae_sample_bwd(g.data_ptr(), mom.data_ptr(), noise.data_ptr(), dmom.data_ptr(), B, h * w_, 64,
+                                     SCALING, float(clip), GRAD_SCALE * float(scale), st), "vae_sample_bwd")
+        dn = ops.conv3x3(dmom, self.w["conv_out.bwd"])
+        d = ops.groupnorm_bwd(x_out, dn, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"], stn, silu=True, out=dn)
+        for rec in reversed(saved):
+            if rec[0] == "resnet":
+                d = self._resnet_bwd(rec, d)
+            elif rec[0] == "attn":
+                d = self._attn_bwd(rec, d)
+            else:
+                d = self._down_bwd(rec, d)
+        dx16 = ops.conv3x3(d, self.w["conv_in.bwd"])                              # [B,H,W,16], 3 real channels
+        dimg = torch.empty((B, 3, H, W), dtype=torch.float32, device=g.device)
+        ops._chk(L.gd_vae_dimg(dx16.data_ptr(), dimg.data_ptr(), B, H, W, 16, 2.0 / GRAD_SCALE, st), "vae_dimg")
+        return dimg

@@ -125,6 +125,42 @@ int gd_unet_add_noise(const float* latents, const float* noise, const float* sqr
 int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float guidance_scale,
                      float* noise_pred, float* grad, int B, int chw, gd_ustream_t stream);
 
+/* ---- VAE encoder forward + input-gradient backward ------------------------------------------
+ * encode_images (stable_diffusion_guidance.py:160-167): imgs*2-1 -> AutoencoderKL.encode ->
+ * latent_dist.sample() * scaling_factor, differentiated w.r.t. the image by the SDS loss
+ * (:424-427). The reference runs diffusers 0.19.0 AutoencoderKL in fp16 under autograd; here the
+ * convolutions / attention matmuls are gd_unet_gemm calls (dgrad = the same implicit-GEMM with
+ * flipped, transposed weights) and the functions below are the fused sweeps around them. */
+
+/* GroupNorm (+SiLU) for tensors of any size that also returns the statistics the backward
+   needs: stats fp32 [N*groups][2] = (mean, rstd). y may be NULL (statistics only). */
+int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const void* beta, float* stats,
+                            int N, int HW, int C, int groups, float eps, int silu, gd_ustream_t stream);
+/* Backward of z = act(GroupNorm(x)) (act = SiLU if silu else identity) w.r.t. x:
+   dx = dGN(x; stats)^T (dz * act'(y)) (+ add). x, dz, add (may be NULL), dx: fp16 [N,HW,C]. */
+int gd_unet_groupnorm_bwd(const void* x, const void* dz, const void* add, void* dx, const void* gamma,
+                          const void* beta, const float* stats, int N, int HW, int C, int groups, int silu,
+                          gd_ustream_t stream);
+/* In-place softmax backward: dP <- P * (dP - rowsum(P * dP)); fp16 [rows, cols], row stride ld. */
+int gd_unet_softmax_bwd(const void* P, void* dP, long long rows, int cols, long long ld, gd_ustream_t stream);
+/* Batched transpose fp16: x [B,R,C] -> y [B,C,R]. */
+int gd_unet_transpose(const void* x, void* y, int B, int R, int C, gd_ustream_t stream);
+/* Inverse of gd_unet_space_to_depth: [N,H/2,W/2,4C] -> [N,H,W,C]. */
+int gd_unet_depth_to_space(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t stream);
+/* color fp32 NCHW [B,3,H,W] in [0,1] -> fp16 NCHW [B,4,H,W] = (2*color-1 | 0): conv_in input. */
+int gd_vae_prep(const float* color_nchw, void* y, int B, int H, int W, gd_ustream_t stream);
+/* DiagonalGaussianDistribution.sample() * scaling: moments fp16 NHWC [B,hw,8] (mean | logvar,
+   logvar clamped to [-30,20]), noise fp32 NCHW [B,4,hw] -> latents fp32 NCHW [B,4,hw]. */
+int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling,
+                  gd_ustream_t stream);
+/* Its backward: grad fp32 NCHW (nan_to_num, clamp to +-clip if clip > 0, * scaling * gscale)
+   -> d moments fp16 NHWC [B,hw,Cp] (8 real channels, zero padded to Cp). */
+int gd_vae_sample_bwd(const float* grad, const void* moments, const float* noise, void* dmoments, int B,
+                      int hw, int Cp, float scaling, float clip, float gscale, gd_ustream_t stream);
+/* d image: fp16 NHWC [B,H,W,Cp] (3 real channels) -> fp32 NCHW [B,3,H,W] * scale. */
+int gd_vae_dimg(const void* dx, float* dcolor_nchw, int B, int H, int W, int Cp, float scale,
+                gd_ustream_t stream);
+
 /* Bench glue, NOT part of the reference path: a fixed linear stand-in for the VAE encoder that
    the reference runs between the rasteriser and compute_grad_sds (encode_images, :160-167; out of
    this build's scope). latents [B,4,H/8,W/8] = mix[4][3] * mean_8x8(2*color-1); _bwd is its exact
