@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--phase", default="auto", choices=["auto", "raster", "sds"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="replace the VAE encoder by the linear stand-in")
     return ap.parse_args()
 
 
@@ -150,7 +151,13 @@ def cpu_unet_sample(a):
         return 0.0, ""
     torch.set_num_threads(os.cpu_count())
     s = unet_ref.time_cpu_forward(batch=2)
-    return s * a.views, f"; UNet fp32 eager on CPU: batch 2 timed ({s:.1f}s), x{a.views} extrapolated"
+    total, note = s * a.views, f"; UNet fp32 eager on CPU: batch 2 timed ({s:.1f}s), x{a.views} extrapolated"
+    if not a.no_vae:
+        from oracle import vae_ref
+        v = vae_ref.time_cpu_encode(batch=1, res=a.res)
+        total += v * a.views
+        note += f"; VAE encode + input-gradient fp32 eager on CPU: 1 image timed ({v:.1f}s), x{a.views} extrapolated"
+    return total, note
 
 
 def unet_available():
@@ -158,6 +165,9 @@ def unet_available():
 
 
 def workload_name(a, with_unet):
+    if with_unet and not a.no_vae:
+        return (f"c2: {a.P} Gaussians, {a.views}x{a.res}^2 views per GPU, full SDS loop: raster fwd + VAE encode + SD-2.1 UNet "
+                f"SDS grad (batch {2 * a.views}) + VAE input-gradient bwd + raster bwd (random-init fp16 networks)"), True
     if with_unet:
         return (f"c2: {a.P} Gaussians, {a.views}x{a.res}^2 views per GPU, raster fwd + SD-2.1 UNet SDS grad "
                 f"(batch {2 * a.views}, random-init fp16) + raster bwd; VAE excluded (latents = 8x8-pooled render)"), True
@@ -186,7 +196,7 @@ def main():
     guidance = None
     if with_unet:
         from garmentdreamer_b200 import sds_step
-        guidance = sds_step.make_bench_guidance(dev, a.views)
+        guidance = sds_step.make_bench_guidance(dev, a.views, use_vae=not a.no_vae)
     workload, _ = workload_name(a, with_unet)
 
     P, B, S = a.P, a.views, a.res
@@ -276,6 +286,7 @@ def main():
     dev_ms = sum(x.elapsed_time(y) for x, y in step_ms)
     bwd_ms = float(np.mean([x.elapsed_time(y) for x, y in timers["ev"]]))
     sds_roofline = guidance.roofline(*measured_peaks()) if guidance is not None else None
+    vae_ms = guidance.vae_ms() if guidance is not None else (0.0, 0.0)
     # ---- end to end through the public API with host buffers (`e2e`) ----
     barrier()
     t_e2e = []
@@ -313,6 +324,14 @@ def main():
     if sds_roofline is not None:
         sds_roofline["raster_bwd"] = roofline
         roofline = sds_roofline
+        if guidance.vae is not None:
+            from garmentdreamer_b200 import sds_step as _s
+            roofline["vae"] = {"bound": "tensor", "kernel": "VAE encode + input-gradient backward (k_gemm_tcgen05 conv-GEMM + GroupNorm sweeps)",
+                               "encode_ms": vae_ms[0], "backward_ms": vae_ms[1],
+                               "achieved": (_s.VAE_FWD_FLOPS_PER_IMAGE + _s.VAE_BWD_FLOPS_PER_IMAGE) * B * (S / 512.0) ** 2
+                               / ((vae_ms[0] + vae_ms[1]) * 1e-3) / 1e12,
+                               "peak": peaks.get("bf16_tflops_sustained"), "unit": "TFLOP/s"}
+            roofline["vae"]["frac"] = roofline["vae"]["achieved"] / roofline["vae"]["peak"]
     line = {
         "metric": "SDS iterations/sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(3, a.warmup), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,

@@ -46,6 +46,8 @@ struct GemmKParams {
   int block_n;
   int stages;
   int m_tiles, n_tiles, total_tiles;
+  int stg_bufs;               // staging buffers per epilogue warp (1 or 2; 0 = no staging area)
+  int tma_store;              // MODE 0: full 32-column chunks leave through shared memory + TMA store (tmC)
   int ksplit, kb_per_split;   // split-K: tile t covers k-blocks [ks*kb_per_split, ...) and writes fp32 partials
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
 };
@@ -82,6 +84,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
           "r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
+          "l"(map), "r"(s2u(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart): UMMA smem
 // descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO 1 | SBO 1024>>4 | version 1 | SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -106,7 +114,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // Persistent, warp-specialised: grid = min(tiles, SMs). The accumulator is double-buffered in
 // TMEM so the epilogue of tile i overlaps the main loop of tile i+1; the TMA ring runs ahead
@@ -116,13 +124,15 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // 3 split-K fp32 partials. One instantiation per mode keeps each kernel's code small (I-cache).
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.block_n, S = p.stages;
   const uint32_t a_bytes = kBM * kBK * 2, b_bytes = (uint32_t)BN * kBK * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint8_t* stg_all = smem + (size_t)S * stage_bytes;   // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + (size_t)kEpiWarps * p.stg_bufs * 2048);
   uint64_t* empty = full + S;
   uint64_t* tmem_full = empty + S;      // [2]
   uint64_t* tmem_empty = tmem_full + 2; // [2]
@@ -227,6 +237,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool geglu = MODE == 1, transposed = MODE == 2, splitk = MODE == 3;
     const int chunks = (BN + 31) / 32;
     float* sb = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * 128;   // [4 chunks][32] bias sums
+    // output staging for the TMA store: 2 x [32 rows x 64 B] per warp, 64B-swizzled, 1024-aligned
+    uint8_t* stg_base = stg_all + (size_t)(warp - 2) * p.stg_bufs * 2048;
+    uint32_t st_cnt = 0;
+    if (MODE == 0 && p.tma_store && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     const bool vec_ok = (p.ldc & 7) == 0 && MODE == 0;
     int lt = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
@@ -290,8 +304,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
         }
         const int n0 = n_blk * BN + c0;
-        if (!row_ok || n0 >= nlim) continue;
+        if (n0 >= nlim) continue;                 // warp-uniform
         const bool full32 = n0 + 32 <= nlim;
+        if (!(MODE == 0 && p.tma_store && full32) && !row_ok) continue;   // the TMA path needs the whole warp
         if constexpr (splitk) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
           float* wdst = p.ws + ((size_t)ks * p.M + row) * p.N + n0;
           if (full32) {
@@ -331,7 +346,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           __half* dst = p.C + coff + (long long)row * p.ldc + n0;
           if (full32 && (p.ldc & 7) == 0) {
-            __align__(16) __half o[32];
+            uint4 o[4];
             if (p.residual) {
               const __half* rh = reinterpret_cast<const __half*>(&rcur[0]);
 #pragma unroll
@@ -342,12 +357,38 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 32; j++) v[j] = silu(v[j]);
             }
 #pragma unroll
-            for (int j = 0; j < 32; j++) o[j] = __float2half_rn(v[j]);
+            for (int u = 0; u < 4; u++) {
+              __half2 h0 = __floats2half2_rn(v[8 * u], v[8 * u + 1]), h1 = __floats2half2_rn(v[8 * u + 2], v[8 * u + 3]);
+              __half2 h2 = __floats2half2_rn(v[8 * u + 4], v[8 * u + 5]), h3 = __floats2half2_rn(v[8 * u + 6], v[8 * u + 7]);
+              o[u] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+            if (p.tma_store) {
+              // registers -> swizzled staging tile -> one bulk tensor store per chunk (coalesced, async;
+              // rows beyond M are clipped by the tensor map)
+              uint8_t* stg = stg_base + (p.stg_bufs == 2 ? (st_cnt & 1u) * 2048 : 0u);
+              if (lane == 0) {   // the buffer's previous store has finished reading it
+                if (p.stg_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = reinterpret_cast<const uint4*>(o)[u];
+              for (int u = 0; u < 4; u++)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o[u];
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmC, stg, n0, m_blk * kBM + q * 32, zh, zb);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              st_cnt++;
+            } else if (row_ok) {
+#pragma unroll
+              for (int u = 0; u < 4; u++) reinterpret_cast<uint4*>(dst)[u] = o[u];
+            }
           } else {
             const __half* res = p.residual ? p.residual + coff + (long long)row * p.ldc + n0 : nullptr;
-#pragma unroll 1
+#pragma unroll   // static register indices (a rolled loop would spill v[] to local memory)
             for (int j = 0; j < 32; j++) {
               if (n0 + j < nlim) {
                 float x = v[j] + (res ? __half2float(res[j]) : 0.0f);
@@ -364,6 +405,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
+  if (MODE == 0 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging reads + writes done
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {

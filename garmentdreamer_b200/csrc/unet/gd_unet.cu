@@ -40,12 +40,12 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-             const cuuint32_t* box) {
+             const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(GD_UNET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
-                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u",
@@ -602,10 +602,22 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
-  int stages = (int)((196 * 1024) / stage_bytes);   // one persistent CTA per SM owns the shared memory
+  // one persistent CTA per SM owns the shared memory: operand ring + epilogue staging + barriers/bias
+  const size_t smem_max = 227 * 1024, fixed = 1024 + 256 + 64 + gdu::kEpiWarps * 128 * sizeof(float);
+  const bool mode0 = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED));
+  const bool tma_ok = mode0 && (a->ldc % 8) == 0 && (a->c_batch_stride % 8) == 0 && (a->c_head_stride % 8) == 0 &&
+                      ((uintptr_t)a->C % 16) == 0 && (a->heads == 1 || a->c_head_stride > 0) &&
+                      (a->batch == a->heads || a->c_batch_stride > 0);
+  int stg_bufs = tma_ok ? 2 : 0;
+  int stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
+  if (tma_ok && stages < 4) {
+    stg_bufs = 1;
+    stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
+  }
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
+  p.stg_bufs = stg_bufs;
   p.m_tiles = (a->M + gdu::kBM - 1) / gdu::kBM;
   p.n_tiles = (a->N + BN - 1) / BN;
   p.ksplit = 1; p.kb_per_split = p.num_kb; p.ws = nullptr;
@@ -631,7 +643,20 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     }
   }
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
-  const size_t smem = stages * stage_bytes + 1024 + 256 + gdu::kEpiWarps * 128 * sizeof(float) + 64;
+  const size_t smem = stages * stage_bytes + (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed;
+  // output tensor map for the staged epilogue: [batch][head][M][N], 32 x 32 box, 64B swizzle
+  CUtensorMap tmC = tmA;
+  p.tma_store = 0;
+  if (tma_ok && p.ksplit == 1) {
+    const cuuint64_t row_b = (cuuint64_t)a->ldc * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)a->N, (cuuint64_t)a->M, (cuuint64_t)a->heads, (cuuint64_t)(a->batch / a->heads)};
+    cuuint64_t str[3] = {row_b, a->heads > 1 ? (cuuint64_t)a->c_head_stride * 2 : row_b,
+                         a->batch > a->heads ? (cuuint64_t)a->c_batch_stride * 2 : row_b};
+    cuuint32_t box[4] = {32, 32, 1, 1};
+    const int rc = make_map(&tmC, a->C, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != GD_UNET_OK) return rc;
+    p.tma_store = 1;
+  }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -644,10 +669,10 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
       return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  if (p.ksplit > 1) launch_pdl(gdu::k_gemm_tcgen05<3>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
-  else if (a->flags & GD_EPI_GEGLU) launch_pdl(gdu::k_gemm_tcgen05<1>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
-  else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl(gdu::k_gemm_tcgen05<2>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
-  else launch_pdl(gdu::k_gemm_tcgen05<0>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, p);
+  if (p.ksplit > 1) launch_pdl(gdu::k_gemm_tcgen05<3>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
+  else if (a->flags & GD_EPI_GEGLU) launch_pdl(gdu::k_gemm_tcgen05<1>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
+  else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl(gdu::k_gemm_tcgen05<2>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
+  else launch_pdl(gdu::k_gemm_tcgen05<0>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
   LAUNCH_CHECK("k_gemm_tcgen05");
   if (p.ksplit > 1) {
     const long long n4 = (long long)a->M * a->N / 4;
@@ -822,6 +847,16 @@ float2* gn_part_buffer() {   // partial statistics: up to 8192 (image, group) x 
   if (!part && cudaMalloc(&part, sizeof(float2) * 8192 * 512) != cudaSuccess) return nullptr;
   return part;
 }
+// pixels per CTA of the fast sweeps: up to 128 K elements per CTA, but at least ~600 CTAs
+int gn_fast_pix_per_cta(int N, int HW, int C, int unroll) {
+  const int step = (256 / (C / 8)) * unroll;             // pixels one CTA iteration covers
+  long long ppc = 131072 / C;
+  const long long fill = ((long long)N * HW + 599) / 600;
+  if (ppc > fill) ppc = fill;
+  if (ppc < step) ppc = step;
+  ppc = (ppc + step - 1) / step * step;
+  return (int)ppc;
+}
 int gn_big_splits(int N, int HW, int C) {
   long long per = 4096;                                    // ~4096 sixteen-byte loads per CTA
   long long splits = ((long long)HW * (C / 8) + per - 1) / per;
@@ -844,10 +879,22 @@ int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const voi
   launch_pdl(gdu::k_gn_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, part, HW, C, groups, splits);
   LAUNCH_CHECK("k_gn_stats");
   const int total = N * groups;
-  launch_pdl(gdu::k_gn_finalize, dim3((total + 255) / 256), dim3(256), (size_t)0, s, (const float2*)part, (float2*)stats, total,
+  launch_pdl(gdu::k_gn_finalize, dim3((total + 7) / 8), dim3(256), (size_t)0, s, (const float2*)part, (float2*)stats, total,
              splits, 1.0f / ((float)HW * (float)(C / groups)), eps);
   LAUNCH_CHECK("k_gn_finalize");
   if (y) {
+    const int C8 = C / 8;
+    if (256 % C8 == 0) {   // fast sweep: 4 loads in flight per thread
+      int pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 4);
+      const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+      if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
+      if (silu) launch_pdl(gdu::k_gn_apply_fast<true, 4>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
+                           (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
+      else launch_pdl(gdu::k_gn_apply_fast<false, 4>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
+                      (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
+      LAUNCH_CHECK("k_gn_apply_fast");
+      return GD_UNET_OK;
+    }
     int pix_per_cta = (32768 + C - 1) / C;
     const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
     if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
@@ -872,12 +919,24 @@ int gd_unet_groupnorm_bwd(const void* x, const void* dz, const void* add, void* 
              (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits, silu);
   LAUNCH_CHECK("k_gn_bwd_stats");
   const int total = N * groups;
-  launch_pdl(gdu::k_gn_bwd_finalize, dim3((total + 255) / 256), dim3(256), (size_t)0, s, (const float2*)part, bstats, total, splits,
+  launch_pdl(gdu::k_gn_bwd_finalize, dim3((total + 7) / 8), dim3(256), (size_t)0, s, (const float2*)part, bstats, total, splits,
              1.0f / ((float)HW * (float)(C / groups)));
   LAUNCH_CHECK("k_gn_bwd_finalize");
   int pix_per_cta = (32768 + C - 1) / C;
   const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
   if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: image too large");
+  if (256 % (C / 8) == 0) {
+    pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 2);
+    const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+    if (silu) launch_pdl(gdu::k_gn_bwd_apply_fast<true, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
+                         (const __half*)add, (__half*)dx, (const float2*)stats, (const float2*)bstats, (const __half*)gamma,
+                         (const __half*)beta, HW, C, groups, pix_per_cta);
+    else launch_pdl(gdu::k_gn_bwd_apply_fast<false, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
+                    (const __half*)add, (__half*)dx, (const float2*)stats, (const float2*)bstats, (const __half*)gamma,
+                    (const __half*)beta, HW, C, groups, pix_per_cta);
+    LAUNCH_CHECK("k_gn_bwd_apply_fast");
+    return GD_UNET_OK;
+  }
   launch_pdl(gdu::k_gn_bwd_apply, dim3(N, (unsigned)chunks), dim3(256), (size_t)((sizeof(float4) + sizeof(float2)) * C), s, (const __half*)x,
              (const __half*)dz, (const __half*)add, (__half*)dx, (const float2*)stats, (const float2*)bstats, (const __half*)gamma,
              (const __half*)beta, HW, C, groups, silu, pix_per_cta);
@@ -905,9 +964,9 @@ int gd_unet_depth_to_space(const void* x, void* y, int N, int H, int W, int C, g
   LAUNCH_CHECK("k_depth_to_space");
   return GD_UNET_OK;
 }
-int gd_vae_prep(const float* color, void* y, int B, int H, int W, gd_ustream_t s) {
+int gd_vae_prep(const float* color, void* y, int B, int H, int W, float a, float shift, gd_ustream_t s) {
   const long long n = (long long)B * 4 * H * W;
-  launch_pdl(gdu::k_vae_prep, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, color, (__half*)y, B, (long long)H * W);
+  launch_pdl(gdu::k_vae_prep, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, color, (__half*)y, B, (long long)H * W, a, shift);
   LAUNCH_CHECK("k_vae_prep");
   return GD_UNET_OK;
 }

@@ -10,18 +10,26 @@
 namespace gdu {
 
 // ---- GroupNorm statistics, finalised: stats[n*groups+g] = (mean, rstd) -----------------------
+// One warp per (image, group): lanes stride over the splits (loads in flight), then a fixed-order
+// xor-shuffle tree => deterministic.
+__device__ __forceinline__ float2 warp_sum_parts(const float2* __restrict__ part, int splits, int lane) {
+  float s = 0.f, ss = 0.f;
+  for (int k = lane; k < splits; k += 32) {
+    const float2 p = part[k];
+    s += p.x; ss += p.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
+  return make_float2(s, ss);
+}
 __global__ void __launch_bounds__(256)
 k_gn_finalize(const float2* __restrict__ part, float2* __restrict__ stats, int total, int splits, float inv_n, float eps) {
   pdl_entry();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= total) return;
-  float s = 0.f, ss = 0.f;
-  for (int k = 0; k < splits; k++) {   // fixed order: deterministic
-    const float2 p = part[(size_t)i * splits + k];
-    s += p.x; ss += p.y;
-  }
-  const float mean = s * inv_n;
-  stats[i] = make_float2(mean, rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + eps));
+  const float2 t = warp_sum_parts(part + (size_t)i * splits, splits, lane);
+  const float mean = t.x * inv_n;
+  if (lane == 0) stats[i] = make_float2(mean, rsqrtf(fmaxf(t.y * inv_n - mean * mean, 0.0f) + eps));
 }
 
 // y = GN(x) (+SiLU) with finalised statistics. grid (image, pixel chunks).
@@ -63,7 +71,7 @@ k_gn_apply_final(const __half* __restrict__ x, __half* __restrict__ y, const flo
 // g = dz * act'(y):   dx = rstd * (gamma*g - S1 - xh*S2),  S1 = mean_group(gamma*g),
 // S2 = mean_group(gamma*g*xh).
 __device__ __forceinline__ float dsilu(float y) {
-  const float s = 1.0f / (1.0f + __expf(-y));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-y));
   return s * (1.0f + y * (1.0f - s));
 }
 // Pass 1: same sweep as k_gn_stats; per channel sum(g), sum(g*xh) folded with gamma per group.
@@ -93,7 +101,7 @@ k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dz, cons
       gam[k] = __half2float(gamma[chunk * 8 + k]); bet[k] = __half2float(beta[chunk * 8 + k]);
       s[k] = 0.f; ss[k] = 0.f;
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int pix = p0 + pl; pix < p1; pix += pix_par) {
       const uint4 xv = xb[(size_t)pix * C8 + chunk], gv = gb[(size_t)pix * C8 + chunk];
       const __half2* xh2 = reinterpret_cast<const __half2*>(&xv);
@@ -126,14 +134,10 @@ k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dz, cons
 __global__ void __launch_bounds__(256)
 k_gn_bwd_finalize(const float2* __restrict__ part, float2* __restrict__ bstats, int total, int splits, float inv_n) {
   pdl_entry();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= total) return;
-  float s = 0.f, ss = 0.f;
-  for (int k = 0; k < splits; k++) {
-    const float2 p = part[(size_t)i * splits + k];
-    s += p.x; ss += p.y;
-  }
-  bstats[i] = make_float2(s * inv_n, ss * inv_n);
+  const float2 t = warp_sum_parts(part + (size_t)i * splits, splits, lane);
+  if (lane == 0) bstats[i] = make_float2(t.x * inv_n, t.y * inv_n);
 }
 // Pass 2: dx = rstd*(gamma*g - S1 - xh*S2) (+ add).
 __global__ void __launch_bounds__(256)
@@ -178,6 +182,101 @@ k_gn_bwd_apply(const __half* __restrict__ x, const __half* __restrict__ dz, cons
       ah2[k] = __floats2half2_rn(d0, d1);
     }
     ob[i] = av;
+  }
+}
+
+// ---- fast sweeps for C/8 dividing 256 (C = 64..2048 powers of two: every VAE layer) ----------
+// A thread owns one 8-channel chunk for its whole life (per-channel coefficients in registers,
+// no index arithmetic in the loop) and keeps U independent 16-byte loads per tensor in flight.
+template <bool SILU, int U>
+__global__ void __launch_bounds__(256)
+k_gn_apply_fast(const __half* __restrict__ x, __half* __restrict__ y, const float2* __restrict__ stats,
+                const __half* __restrict__ gamma, const __half* __restrict__ beta, int HW, int C, int groups, int pix_per_cta) {
+  pdl_entry();
+  const int n = blockIdx.x, cpg = C / groups, C8 = C >> 3, PP = 256 / C8;
+  const int ch = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = ch * 8 + k;
+    const float2 mr = stats[(size_t)n * groups + c / cpg];
+    sa[k] = mr.y * __half2float(gamma[c]);
+    sb[k] = __half2float(beta[c]) - mr.x * sa[k];
+  }
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C) + ch;
+  uint4* yb = reinterpret_cast<uint4*>(y + (size_t)n * HW * C) + ch;
+  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) if (pix + u * PP < p1) v[u] = xb[(size_t)(pix + u * PP) * C8];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (pix + u * PP >= p1) break;
+      __half2* h = reinterpret_cast<__half2*>(&v[u]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(h[k]);
+        float a = f.x * sa[2 * k] + sb[2 * k], b = f.y * sa[2 * k + 1] + sb[2 * k + 1];
+        if (SILU) { a = silu(a); b = silu(b); }
+        h[k] = __floats2half2_rn(a, b);
+      }
+      yb[(size_t)(pix + u * PP) * C8] = v[u];
+    }
+  }
+}
+
+template <bool SILU, int U>
+__global__ void __launch_bounds__(256)
+k_gn_bwd_apply_fast(const __half* __restrict__ x, const __half* dz, const __half* __restrict__ add, __half* dx,
+                    const float2* __restrict__ stats, const float2* __restrict__ bstats, const __half* __restrict__ gamma,
+                    const __half* __restrict__ beta, int HW, int C, int groups, int pix_per_cta) {
+  pdl_entry();
+  const int n = blockIdx.x, cpg = C / groups, C8 = C >> 3, PP = 256 / C8;
+  const int ch = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float ca[8], cb[8], cg[8], ce[8], s1[8], s2[8];   // xh = x*ca+cb; y = xh*cg+ce; dx = ca*cg*g - s1 - xh*s2
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = ch * 8 + k;
+    const float2 mr = stats[(size_t)n * groups + c / cpg], bs = bstats[(size_t)n * groups + c / cpg];
+    ca[k] = mr.y; cb[k] = -mr.x * mr.y;
+    cg[k] = __half2float(gamma[c]); ce[k] = __half2float(beta[c]);
+    s1[k] = mr.y * bs.x; s2[k] = mr.y * bs.y;
+  }
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const size_t base = (size_t)n * HW * C;
+  const uint4* xb = reinterpret_cast<const uint4*>(x + base) + ch;
+  const uint4* gb = reinterpret_cast<const uint4*>(dz + base) + ch;
+  const uint4* ab = add ? reinterpret_cast<const uint4*>(add + base) + ch : nullptr;
+  uint4* ob = reinterpret_cast<uint4*>(dx + base) + ch;
+  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
+    uint4 xv[U], gv[U], av[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const bool ok = pix + u * PP < p1;
+      const size_t o = (size_t)(pix + u * PP) * C8;
+      xv[u] = ok ? xb[o] : make_uint4(0, 0, 0, 0);
+      gv[u] = ok ? gb[o] : make_uint4(0, 0, 0, 0);
+      av[u] = (ok && ab) ? ab[o] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (pix + u * PP >= p1) break;
+      const __half2* xh2 = reinterpret_cast<const __half2*>(&xv[u]);
+      const __half2* gh2 = reinterpret_cast<const __half2*>(&gv[u]);
+      __half2* ah2 = reinterpret_cast<__half2*>(&av[u]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 xf = __half22float2(xh2[k]), gf = __half22float2(gh2[k]), af = __half22float2(ah2[k]);
+        const float xh0 = xf.x * ca[2 * k] + cb[2 * k], xh1 = xf.y * ca[2 * k + 1] + cb[2 * k + 1];
+        float g0 = gf.x, g1 = gf.y;
+        if (SILU) { g0 *= dsilu(xh0 * cg[2 * k] + ce[2 * k]); g1 *= dsilu(xh1 * cg[2 * k + 1] + ce[2 * k + 1]); }
+        const float d0 = ca[2 * k] * cg[2 * k] * g0 - s1[2 * k] - xh0 * s2[2 * k] + af.x;
+        const float d1 = ca[2 * k + 1] * cg[2 * k + 1] * g1 - s1[2 * k + 1] - xh1 * s2[2 * k + 1] + af.y;
+        ah2[k] = __floats2half2_rn(d0, d1);
+      }
+      ob[(size_t)(pix + u * PP) * C8] = av[u];
+    }
   }
 }
 
@@ -257,14 +356,14 @@ __global__ void k_depth_to_space(const uint4* __restrict__ x, uint4* __restrict_
   y[i] = x[((((long long)n * (H >> 1) + (iy >> 1)) * (W >> 1) + (ix >> 1)) * 4 + ph) * C8 + c];
 }
 
-// ---- image pre-processing: color fp32 NCHW [B,3,H,W] in [0,1] -> fp16 NCHW [B,4,H,W] = 2c-1 | 0 ----
-__global__ void k_vae_prep(const float* __restrict__ color, __half* __restrict__ y, int B, long long HW) {
+// ---- image pre-processing: color fp32 NCHW [B,3,H,W] -> fp16 NCHW [B,4,H,W] = a*c+sh | 0 ----
+__global__ void k_vae_prep(const float* __restrict__ color, __half* __restrict__ y, int B, long long HW, float a, float sh) {
   pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * 4 * HW) return;
   const long long p = i % HW;
   const int c = (int)((i / HW) % 4), b = (int)(i / (4 * HW));
-  y[i] = __float2half_rn(c < 3 ? 2.0f * color[((long long)b * 3 + c) * HW + p] - 1.0f : 0.0f);
+  y[i] = __float2half_rn(c < 3 ? a * color[((long long)b * 3 + c) * HW + p] + sh : 0.0f);
 }
 // ---- DiagonalGaussianDistribution.sample() * scaling: moments fp16 NHWC [B,h,w,8] (mean|logvar) ----
 __global__ void k_vae_sample(const __half* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ lat,

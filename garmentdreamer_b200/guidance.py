@@ -8,9 +8,10 @@ Mirrors (names, argument meaning, return values, error behaviour):
         Garment_3DGS/threestudio/models/guidance/stable_diffusion_guidance.py:141-157,185-276,
         374-448,581-591
 The UNet behind ``self.unet`` is garmentdreamer_b200.unet.UNetB200 (tcgen05 kernels). The noise
-add and the CFG/SDS epilogue run as fused CUDA kernels of libgd_unet.so. The VAE (encode_images)
-is outside north_star's kernel list: ``__call__`` accepts any object with
-``encode(imgs)`` through ``vae=``, or ``rgb_as_latents=True``.
+add and the CFG/SDS epilogue run as fused CUDA kernels of libgd_unet.so. encode_images (SURVEY.md
+s.8 row f1) runs on garmentdreamer_b200.vae.VAEEncoderB200 (forward + input-gradient backward
+behind a torch.autograd.Function) when one is passed through ``vae=``; ``rgb_as_latents=True``
+skips it as in the reference.
 """
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Tuple
@@ -240,10 +241,20 @@ class StableDiffusionGuidance:
         return grad, guidance_eval_utils
 
     def encode_images(self, imgs):
+        """stable_diffusion_guidance.py:160-167. With a VAEEncoderB200 attached the whole function
+        (imgs*2-1, encoder, sample, scaling) and its backward are CUDA kernels of libgd_unet.so;
+        any other object is driven through the diffusers surface exactly like the reference."""
         if self.vae is None:
-            raise RuntimeError("no VAE attached: pass vae= (object with encode(imgs)->latents) or use "
-                               "rgb_as_latents=True; the VAE is outside this build's scope (SURVEY.md s.8 f1)")
-        return self.vae.encode(imgs * 2.0 - 1.0)
+            raise RuntimeError("no VAE attached: pass vae=VAEEncoderB200(...) (or an object with the diffusers "
+                               "encode(...).latent_dist.sample() surface), or use rgb_as_latents=True")
+        from .vae import VAEEncoderB200
+        if isinstance(self.vae, VAEEncoderB200):
+            return self.vae.encode_images(imgs, generator=self.generator)
+        input_dtype = imgs.dtype
+        imgs = imgs * 2.0 - 1.0
+        posterior = self.vae.encode(imgs.to(self.weights_dtype)).latent_dist
+        latents = posterior.sample() * self.vae.config.scaling_factor
+        return latents.to(input_dtype)
 
     def __call__(self, rgb, prompt_utils, elevation, azimuth, camera_distances, rgb_as_latents=False,
                  guidance_eval=False, **kwargs):

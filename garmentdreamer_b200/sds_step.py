@@ -1,12 +1,13 @@
-"""One SDS step on rendered views, as bench.py times it (BASELINE config 2 with the VAE excluded):
+"""One SDS step on rendered views, as bench.py times it (BASELINE config 2):
 
-    colour [B,3,S,S] --(linear stand-in for the VAE encoder)--> latents [B,4,S/8,S/8]
+    colour [B,3,S,S] --VAE encoder (VAEEncoderB200.encode: 2c-1, encoder, sample, x0.18215)-->
+      latents [B,4,S/8,S/8]
       --> StableDiffusionGuidance.compute_grad_sds (B200 UNet, batch 2B) --> grad
-      --> nan_to_num / clamp / 1/B (guidance __call__, :418-427) --> dL/dcolour [B,3,S,S]
+      --> nan_to_num / clamp / 1/B (guidance __call__, :418-427)
+      --> VAE encoder input-gradient backward --> dL/dcolour [B,3,S,S]
 
-The stand-in (8x8 mean of 2*rgb-1 and a fixed 3->4 channel mix) is NOT the reference's VAE; the
-VAE encoder is row f1 ("next") of SURVEY.md s.8 and every number produced through this module says
-"VAE excluded" in its config.
+With ``use_vae=False`` the encoder is replaced by a linear stand-in (8x8 mean of 2*rgb-1 and a
+fixed 3->4 channel mix); numbers produced that way say "VAE excluded" in their config.
 """
 import torch
 
@@ -15,6 +16,10 @@ from .guidance import PromptProcessorOutput, StableDiffusionGuidance
 from .unet import UNetB200
 
 UNET_FLOPS_PER_SAMPLE = 804.3e9  # SURVEY.md Appendix B (conv 418.4 + linear 259.8 + attention 126.1 GFLOP)
+# VAE encoder at 512^2, per image, forward (conv 1057.6 + linear/1x1 17.2 + attention matmuls 34.4 GFLOP);
+# the input-gradient backward repeats every contraction once (dgrad) and the attention matmuls twice
+VAE_FWD_FLOPS_PER_IMAGE = 1109.2e9
+VAE_BWD_FLOPS_PER_IMAGE = 1109.2e9 + 34.4e9
 
 
 def _random_state_dict(seed, device):
@@ -23,9 +28,15 @@ def _random_state_dict(seed, device):
 
 
 class SdsBenchStep:
-    def __init__(self, dev, views, state_dict=None, seed=0, use_cuda_graph=True):
+    def __init__(self, dev, views, state_dict=None, seed=0, use_cuda_graph=True, use_vae=True):
         self.dev = torch.device(dev)
         self.B = views
+        self.vae = None
+        if use_vae:
+            from .unet_init import random_vae_state_dict
+            from .vae import VAEEncoderB200
+            self.vae = VAEEncoderB200(random_vae_state_dict(seed, self.dev), self.dev)
+        self._vae_ms = []
         sd = state_dict if state_dict is not None else _random_state_dict(seed, self.dev)
         self.unet = UNetB200(sd, self.dev, use_cuda_graph=use_cuda_graph)
         g = torch.Generator().manual_seed(1234 + seed)
@@ -44,27 +55,45 @@ class SdsBenchStep:
         B, _, H, W = color.shape
         L = ops.lib()
         stream = torch.cuda.current_stream().cuda_stream
-        lat = torch.empty((B, 4, H // 8, W // 8), dtype=torch.float32, device=color.device)
-        ops._chk(L.gd_unet_pool_latents(color.data_ptr(), self.mix.data_ptr(), lat.data_ptr(), B, H, W, stream), "pool_latents")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        if self.vae is not None:
+            noise = torch.randn((B, 4, H // 8, W // 8), device=color.device, dtype=torch.float32, generator=self.gen)
+            lat = self.vae.encode(color, noise)
+        else:
+            lat = torch.empty((B, 4, H // 8, W // 8), dtype=torch.float32, device=color.device)
+            ops._chk(L.gd_unet_pool_latents(color.data_ptr(), self.mix.data_ptr(), lat.data_ptr(), B, H, W, stream), "pool_latents")
         t = torch.randint(self.guidance.min_step, self.guidance.max_step + 1, [B], dtype=torch.long, device=color.device,
                           generator=self.gen)
         elev = torch.tensor([c.elevation_deg for c in cams], device=color.device)
         azim = torch.tensor([c.azimuth_deg for c in cams], device=color.device)
         dist = torch.tensor([c.distance for c in cams], device=color.device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ev[1].record()
         grad, _ = self.guidance.compute_grad_sds(lat, t, self.prompt, elev, azim, dist)
-        e1.record()
-        self._unet_ms.append((e0, e1))
+        ev[2].record()
+        self._unet_ms.append((ev[1], ev[2]))
         self.last_grad = grad
-        dcol = torch.empty_like(color)
-        ops._chk(L.gd_unet_pool_latents_bwd(grad.data_ptr(), self.mix.data_ptr(), dcol.data_ptr(), B, H, W,
-                                            float(self.guidance.grad_clip_val or 0.0), 1.0 / B, stream), "pool_latents_bwd")
+        clip = float(self.guidance.grad_clip_val or 0.0)
+        if self.vae is not None:
+            dcol = self.vae.backward(grad, clip=clip, scale=1.0 / B)
+        else:
+            dcol = torch.empty_like(color)
+            ops._chk(L.gd_unet_pool_latents_bwd(grad.data_ptr(), self.mix.data_ptr(), dcol.data_ptr(), B, H, W, clip, 1.0 / B,
+                                                stream), "pool_latents_bwd")
+        ev[3].record()
+        self._vae_ms.append((ev[0], ev[1], ev[2], ev[3]))
         return dcol
 
     def reset_counters(self):
         self._launch0 = ops.lib().gd_unet_launch_count()
         self._unet_ms = []
+        self._vae_ms = []
+
+    def vae_ms(self):
+        """(encode ms, backward ms) averaged over the steps since reset (0, 0 with the stand-in)."""
+        n = max(1, len(self._vae_ms))
+        return (float(sum(e[0].elapsed_time(e[1]) for e in self._vae_ms) / n),
+                float(sum(e[2].elapsed_time(e[3]) for e in self._vae_ms) / n))
 
     def launch_count_delta(self):
         """Kernels of libgd_unet.so launched since reset; a CUDA-graph replay re-launches the
@@ -90,5 +119,5 @@ class SdsBenchStep:
         return r
 
 
-def make_bench_guidance(dev, views):
-    return SdsBenchStep(dev, views)
+def make_bench_guidance(dev, views, use_vae=True):
+    return SdsBenchStep(dev, views, use_vae=use_vae)

@@ -89,3 +89,64 @@ def random_state_dict(seed=0, device="cpu", dtype=torch.float16):
             v = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
         sd[name] = v.to(device=device, dtype=dtype)
     return sd
+
+
+# ---- SD-2.1 AutoencoderKL encoder (+ quant_conv): 34,163,664 parameters -------------------------
+VAE_CH = (128, 256, 512, 512)
+
+
+def vae_encoder_param_shapes():
+    """diffusers key scheme of AutoencoderKL.encoder + quant_conv (block_out_channels
+    (128,256,512,512), layers_per_block 2, latent_channels 4)."""
+    s = OrderedDict()
+
+    def conv(n, cin, cout, k):
+        s[n + ".weight"] = (cout, cin, k, k)
+        s[n + ".bias"] = (cout,)
+
+    def norm(n, c):
+        s[n + ".weight"] = (c,)
+        s[n + ".bias"] = (c,)
+
+    def resnet(p, cin, cout):
+        norm(p + ".norm1", cin); conv(p + ".conv1", cin, cout, 3)
+        norm(p + ".norm2", cout); conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".conv_shortcut", cin, cout, 1)
+
+    conv("encoder.conv_in", 3, VAE_CH[0], 3)
+    cin = VAE_CH[0]
+    for i, c in enumerate(VAE_CH):
+        for j in range(2):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else c, c)
+        if i < 3:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", c, c, 3)
+        cin = c
+    resnet("encoder.mid_block.resnets.0", 512, 512)
+    a = "encoder.mid_block.attentions.0"
+    norm(a + ".group_norm", 512)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s[f"{a}.{n}.weight"] = (512, 512)
+        s[f"{a}.{n}.bias"] = (512,)
+    resnet("encoder.mid_block.resnets.1", 512, 512)
+    norm("encoder.conv_norm_out", 512)
+    conv("encoder.conv_out", 512, 8, 3)
+    conv("quant_conv", 8, 8, 1)
+    return s
+
+
+def random_vae_state_dict(seed=0, device="cpu", dtype=torch.float32):
+    g = torch.Generator().manual_seed(1000 + seed)
+    sd = OrderedDict()
+    shapes = vae_encoder_param_shapes()
+    for name, shp in shapes.items():
+        if "norm" in name:
+            v = (1.0 if name.endswith("weight") else 0.0) + 0.05 * torch.randn(shp, generator=g)
+        else:
+            wshape = shapes[name[:-4] + "weight"] if name.endswith("bias") else shp
+            fan_in = 1
+            for d in wshape[1:]:
+                fan_in *= d
+            v = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        sd[name] = v.to(device=device, dtype=dtype)
+    return sd

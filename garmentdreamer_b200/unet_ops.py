@@ -73,7 +73,7 @@ def lib():
         L.gd_unet_softmax_bwd.argtypes = [vp, vp, ll, i, ll, vp]
         L.gd_unet_transpose.argtypes = [vp, vp, i, i, i, vp]
         L.gd_unet_depth_to_space.argtypes = [vp, vp, i, i, i, i, vp]
-        L.gd_vae_prep.argtypes = [vp, vp, i, i, i, vp]
+        L.gd_vae_prep.argtypes = [vp, vp, i, i, i, f, f, vp]
         L.gd_vae_sample.argtypes = [vp, vp, vp, i, i, f, vp]
         L.gd_vae_sample_bwd.argtypes = [vp, vp, vp, vp, i, i, i, f, f, f, vp]
         L.gd_vae_dimg.argtypes = [vp, vp, i, i, i, i, f, vp]

@@ -166,19 +166,22 @@ class VAEEncoderB200:
                                  silu=False, add=dout)
 
     # ---- forward / backward ------------------------------------------------------------------
-    def encode(self, imgs01, noise, keep_for_backward=True):
-        """imgs01 fp32 [B,3,H,W] in [0,1] (H, W multiples of 128); noise fp32 [B,4,H/8,W/8] replaces
-        the sampler's randn. Returns latents fp32 [B,4,H/8,W/8]."""
-        if not imgs01.is_cuda:
+    def encode(self, imgs, noise, keep_for_backward=True, input_range="01", scaling=SCALING):
+        """imgs fp32 [B,3,H,W] (H, W multiples of 128), in [0,1] (``input_range="01"``: the
+        `imgs * 2 - 1` of encode_images is fused in) or already in [-1,1] (``"pm1"``); noise fp32
+        [B,4,H/8,W/8] replaces the sampler's randn. Returns fp32 [B,4,H/8,W/8] =
+        posterior.sample() * scaling."""
+        if not imgs.is_cuda:
             raise RuntimeError("garmentdreamer_b200 VAE is CUDA-only (no CPU fallback)")
         L, st = ops.lib(), ops._stream()
-        B, _, H, W = imgs01.shape
+        B, _, H, W = imgs.shape
         if H % 128 or W % 128:
             raise ValueError("VAE encoder: image height / width must be multiples of 128")
-        imgs01 = imgs01.detach().float().contiguous()
+        imgs = imgs.detach().float().contiguous()
         noise = noise.detach().float().contiguous()
-        x4 = torch.empty((B, 4, H, W), dtype=torch.float16, device=imgs01.device)
-        ops._chk(L.gd_vae_prep(imgs01.data_ptr(), x4.data_ptr(), B, H, W, st), "vae_prep")
+        a, sh = (2.0, -1.0) if input_range == "01" else (1.0, 0.0)
+        x4 = torch.empty((B, 4, H, W), dtype=torch.float16, device=imgs.device)
+        ops._chk(L.gd_vae_prep(imgs.data_ptr(), x4.data_ptr(), B, H, W, a, sh, st), "vae_prep")
         saved = []
         x = ops.conv_in(x4, self.w["conv_in.fwd"], self.w["encoder.conv_in.bias"])
         for i in range(4):
@@ -192,24 +195,24 @@ class VAEEncoderB200:
         n, stn = ops.groupnorm_stats(x, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"], eps=EPS, silu=True)
         mom = ops.conv3x3(n, self.w["conv_out.fwd"], self.w["conv_out.bias"])     # [B,h,w,8] = mean | logvar
         h, w_ = H // 8, W // 8
-        lat = torch.empty((B, 4, h, w_), dtype=torch.float32, device=imgs01.device)
-        ops._chk(L.gd_vae_sample(mom.data_ptr(), noise.data_ptr(), lat.data_ptr(), B, h * w_, SCALING, st), "vae_sample")
-        self._saved = (saved, x, stn, mom, noise, (B, H, W)) if keep_for_backward else None
+        lat = torch.empty((B, 4, h, w_), dtype=torch.float32, device=imgs.device)
+        ops._chk(L.gd_vae_sample(mom.data_ptr(), noise.data_ptr(), lat.data_ptr(), B, h * w_, float(scaling), st), "vae_sample")
+        self._saved = (saved, x, stn, mom, noise, (B, H, W), a, float(scaling)) if keep_for_backward else None
         return lat
 
     def backward(self, grad_latents, clip=0.0, scale=1.0):
-        """d<latents, g>/d imgs01 for g = nan_to_num(clamp(grad_latents, +-clip)) * scale
+        """d<latents, g>/d imgs for g = nan_to_num(clamp(grad_latents, +-clip)) * scale
         (stable_diffusion_guidance.py:418-427). fp32 [B,3,H,W]."""
         if self._saved is None:
             raise RuntimeError("VAEEncoderB200.backward() needs a preceding encode(keep_for_backward=True)")
-        saved, x_out, stn, mom, noise, (B, H, W) = self._saved
+        saved, x_out, stn, mom, noise, (B, H, W), a, scaling = self._saved
         self._saved = None
         L, st = ops.lib(), ops._stream()
         h, w_ = H // 8, W // 8
         g = grad_latents.detach().float().contiguous()
         dmom = torch.empty((B, h, w_, 64), dtype=torch.float16, device=g.device)
         ops._chk(L.gd_vae_sample_bwd(g.data_ptr(), mom.data_ptr(), noise.data_ptr(), dmom.data_ptr(), B, h * w_, 64,
-                                     SCALING, float(clip), GRAD_SCALE * float(scale), st), "vae_sample_bwd")
+                                     scaling, float(clip), GRAD_SCALE * float(scale), st), "vae_sample_bwd")
         dn = ops.conv3x3(dmom, self.w["conv_out.bwd"])
         d = ops.groupnorm_bwd(x_out, dn, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"], stn, silu=True, out=dn)
         for rec in reversed(saved):
@@ -221,5 +224,56 @@ class VAEEncoderB200:
                 d = self._down_bwd(rec, d)
         dx16 = ops.conv3x3(d, self.w["conv_in.bwd"])                              # [B,H,W,16], 3 real channels
         dimg = torch.empty((B, 3, H, W), dtype=torch.float32, device=g.device)
-        ops._chk(L.gd_vae_dimg(dx16.data_ptr(), dimg.data_ptr(), B, H, W, 16, 2.0 / GRAD_SCALE, st), "vae_dimg")
+        ops._chk(L.gd_vae_dimg(dx16.data_ptr(), dimg.data_ptr(), B, H, W, 16, a / GRAD_SCALE, st), "vae_dimg")
         return dimg
+
+    # ---- autograd + the diffusers surface the reference calls ---------------------------------
+    def encode_images(self, imgs01, noise=None, generator=None):
+        """Differentiable encode_images (stable_diffusion_guidance.py:160-167): latents carry a
+        grad_fn whose backward is the CUDA input-gradient chain above."""
+        if noise is None:
+            B, _, H, W = imgs01.shape
+            noise = torch.randn((B, 4, H // 8, W // 8), device=imgs01.device, dtype=torch.float32, generator=generator)
+        return _EncodeFn.apply(imgs01, noise, self, "01", SCALING)
+
+
+class _EncodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, imgs, noise, enc, input_range, scaling):
+        ctx.enc = enc
+        ctx.in_dtype = imgs.dtype
+        return enc.encode(imgs, noise, keep_for_backward=True, input_range=input_range, scaling=scaling)
+
+    @staticmethod
+    def backward(ctx, grad_latents):
+        return ctx.enc.backward(grad_latents).to(ctx.in_dtype), None, None, None, None
+
+
+class _LatentDist:
+    def __init__(self, enc, x_pm1):
+        self.enc, self.x = enc, x_pm1
+
+    def sample(self, generator=None):
+        B, _, H, W = self.x.shape
+        noise = torch.randn((B, 4, H // 8, W // 8), device=self.x.device, dtype=torch.float32, generator=generator)
+        return _EncodeFn.apply(self.x.float(), noise, self.enc, "pm1", 1.0).to(self.x.dtype)
+
+
+class DiffusersVAEView:
+    """`pipe.vae` look-alike for the two attributes the reference touches (:165-166):
+    ``vae.encode(imgs_pm1).latent_dist.sample()`` and ``vae.config.scaling_factor``."""
+
+    def __init__(self, enc):
+        from types import SimpleNamespace
+        self.enc = enc
+        self.config = SimpleNamespace(scaling_factor=SCALING)
+
+    def encode(self, x_pm1):
+        from types import SimpleNamespace
+        return SimpleNamespace(latent_dist=_LatentDist(self.enc, x_pm1))
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return self.enc.parameters()

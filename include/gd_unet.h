@@ -147,8 +147,10 @@ int gd_unet_softmax_bwd(const void* P, void* dP, long long rows, int cols, long 
 int gd_unet_transpose(const void* x, void* y, int B, int R, int C, gd_ustream_t stream);
 /* Inverse of gd_unet_space_to_depth: [N,H/2,W/2,4C] -> [N,H,W,C]. */
 int gd_unet_depth_to_space(const void* x, void* y, int N, int H, int W, int C, gd_ustream_t stream);
-/* color fp32 NCHW [B,3,H,W] in [0,1] -> fp16 NCHW [B,4,H,W] = (2*color-1 | 0): conv_in input. */
-int gd_vae_prep(const float* color_nchw, void* y, int B, int H, int W, gd_ustream_t stream);
+/* color fp32 NCHW [B,3,H,W] -> fp16 NCHW [B,4,H,W] = (a*color+shift | 0): conv_in input
+   ((a, shift) = (2, -1) for images in [0,1], the `imgs * 2 - 1` of encode_images). */
+int gd_vae_prep(const float* color_nchw, void* y, int B, int H, int W, float a, float shift,
+                gd_ustream_t stream);
 /* DiagonalGaussianDistribution.sample() * scaling: moments fp16 NHWC [B,hw,8] (mean | logvar,
    logvar clamped to [-30,20]), noise fp32 NCHW [B,4,hw] -> latents fp32 NCHW [B,4,hw]. */
 int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling,
