@@ -313,8 +313,10 @@ def main():
             dist.destroy_process_group()
         return
     peaks, peak_kind = measured_peaks()
-    value = a.steps * 1.0 / (dev_ms * 1e-3)          # iterations/s of the whole job (views sharded)
-    e2e_value = a.steps * 1.0 / (e2e_ms * 1e-3)
+    # one unit = one SDS iteration over B views (BASELINE metric: "4 x 512^2 views"); every rank
+    # processes one unit per step on its own shard of the view batch, so the job does `world` units
+    value = a.steps * world / (dev_ms * 1e-3)
+    e2e_value = a.steps * world / (e2e_ms * 1e-3)
     abytes = algorithmic_bytes_bwd(P * B, R_total, N * B, T * B)
     achieved = abytes / (bwd_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_render_bwd + k_bwd_epilogue (raster backward)",
@@ -339,6 +341,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "P": P, "views_per_gpu": B, "views_total": B * world, "res": S,
                    "num_rendered_rank0": R_total, "l2": "flushed between timed iterations (256 MiB write)",
+                   "unit_of_work": f"one SDS iteration = {B} views; value = ranks x steps / max-over-ranks time",
                    "parallelism": f"views sharded x{world}, NCCL all-reduce of [P,14] grads" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": packed_host.numel() * 4 + cam_host.numel() * 4,
                 "d2h_bytes_per_step": grad_host.numel() * 4},

@@ -109,6 +109,45 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) primitives: two SMs of one TPC compute a 256 x BLOCK_N tile; each CTA
+// stages its own 128 rows of A and HALF of the B tile, the leader (cluster rank 0) issues the MMAs.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cta address -> the leader's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(s2u(dst)), "l"(map), "r"(s2u(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(s2u(dst)), "l"(map), "r"(s2u(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s2u(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void bar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s2u(bar) & kPeerMask) : "memory");
+}
 // Programmatic dependent launch (see launch_pdl in gd_unet.cu)
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -122,14 +161,18 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 // epilogue (two warps per TMEM lane quarter, each takes half of the tile's 32-column chunks).
 // MODE: 0 plain epilogue (bias / time-embedding / residual / SiLU), 1 GEGLU, 2 transposed store,
 // 3 split-K fp32 partials. One instantiation per mode keeps each kernel's code small (I-cache).
-template <int MODE>
+// TWO: CTA-pair version (launched as clusters of 2): tile = 256 x BLOCK_N, per-CTA operand traffic
+// 128 x 64 of A + BLOCK_N/2 x 64 of B per k-block instead of 128 x 64 + BLOCK_N x 64.
+template <int MODE, bool TWO>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.block_n, S = p.stages;
-  const uint32_t a_bytes = kBM * kBK * 2, b_bytes = (uint32_t)BN * kBK * 2;
+  const uint32_t a_bytes = kBM * kBK * 2, b_bytes = (uint32_t)(TWO ? BN / 2 : BN) * kBK * 2;   // per CTA
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
   uint8_t* stg_all = smem + (size_t)S * stage_bytes;   // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + (size_t)kEpiWarps * p.stg_bufs * 2048);
@@ -147,16 +190,21 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < S; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { bar_init(&tmem_full[s], 1); bar_init(&tmem_empty[s], kEpiWarps); }
+    for (int s = 0; s < 2; s++) { bar_init(&tmem_full[s], 1); bar_init(&tmem_empty[s], TWO ? 2 * kEpiWarps : kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(2 * acc_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(2 * acc_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(2 * acc_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised before any remote signal
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel; its results are visible from here on
@@ -165,9 +213,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       int it = 0;  // ring position, runs across tiles
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int t = tile0; t < total; t += tile_step) {
         const int ks = t % p.ksplit, tt = t / p.ksplit;
-        const int n_blk = tt % n_tiles, m_blk = (tt / n_tiles) % m_tiles, z = tt / (n_tiles * m_tiles);
+        const int n_blk = tt % n_tiles, z = tt / (n_tiles * m_tiles);
+        const int m_blk = TWO ? 2 * ((tt / n_tiles) % m_tiles) + (int)rank : (tt / n_tiles) % m_tiles;   // TWO: m_tiles counts pairs
         const int zh = z % p.heads, zb = z / p.heads;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         int a_c1, a_c2, a_c3;
@@ -183,29 +232,41 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           a_c1 = m_blk * kBM; a_c2 = p.a_zflat ? z : zb; a_c3 = 0;
         }
-        const int b_c1 = n_blk * BN + zh * p.b_head_n;
+        const int b_c1 = n_blk * BN + (TWO ? (int)rank * (BN / 2) : 0) + zh * p.b_head_n;
         const int b_c2 = p.b_zdim > 1 ? zb : 0;
         for (int kb = kb0; kb < kb1; kb++, it++) {
           const int s = it % S;
           bar_wait(&empty[s], ((it / S) & 1) ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          bar_expect_tx(&full[s], a_bytes + b_bytes);
-          if (p.mode_conv) {
-            const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
-            tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+          if (TWO) {
+            // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of the pair
+            if (rank == 0) bar_expect_tx(&full[s], 2 * (a_bytes + b_bytes));
+            if (p.mode_conv) {
+              const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
+              tma_load_4d_2sm(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+            } else {
+              tma_load_4d_2sm(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
+            }
+            tma_load_3d_2sm(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, b_c2);
           } else {
-            tma_load_4d(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
+            bar_expect_tx(&full[s], a_bytes + b_bytes);
+            if (p.mode_conv) {
+              const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
+              tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+            } else {
+              tma_load_4d(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
+            }
+            tma_load_3d(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, b_c2);
           }
-          tma_load_3d(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, b_c2);
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t idesc = umma_idesc_f16(BN);
+  } else if (warp == 1 && (!TWO || rank == 0)) {
+    // ---------------- MMA issuer (TWO: the leader CTA only) ----------------
+    const uint32_t idesc = TWO ? (umma_idesc_f16(BN) + ((uint32_t)(kBM >> 4) << 24)) : umma_idesc_f16(BN);   // TWO: M = 256
     int it = 0, lt = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
+    for (int t = tile0; t < total; t += tile_step, lt++) {
       const int acc = lt & 1;
       bar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -219,16 +280,24 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+          if (TWO) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; k++)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
-          umma_commit(&empty[s]);                                   // slot free once these MMAs read it
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);          // accumulator complete
+            for (int k = 0; k < kBK / 16; k++)
+              umma_f16_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
+            umma_commit_2sm(&empty[s]);                             // frees the slot in both CTAs
+            if (kb == kb1 - 1) umma_commit_2sm(&tmem_full[acc]);    // both epilogues
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; k++)  // +32 B per K=16 step inside the 128 B swizzle row
+              umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
+            umma_commit(&empty[s]);                                   // slot free once these MMAs read it
+            if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);          // accumulator complete
+          }
         }
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ---------------- epilogue: warps 2..9; quarter q = warp & 3, column half = (warp - 2) >> 2 ----
     // Per tile a warp owns up to 4 chunks of 32 columns. Everything that does not depend on the
     // accumulator (bias + time-embedding bias -> per-warp shared memory, residual -> registers) is
@@ -243,9 +312,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (MODE == 0 && p.tma_store && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     const bool vec_ok = (p.ldc & 7) == 0 && MODE == 0;
     int lt = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
+    for (int t = tile0; t < total; t += tile_step, lt++) {
       const int ks = t % p.ksplit, tt = t / p.ksplit;
-      const int n_blk = tt % n_tiles, m_blk = (tt / n_tiles) % m_tiles, z = tt / (n_tiles * m_tiles);
+      const int n_blk = tt % n_tiles, z = tt / (n_tiles * m_tiles);
+      const int m_blk = TWO ? 2 * ((tt / n_tiles) % m_tiles) + (int)rank : (tt / n_tiles) % m_tiles;
       const int zh = z % p.heads, zb = z / p.heads;
       const int acc = lt & 1;
       const int row = m_blk * kBM + q * 32 + lane;
@@ -261,7 +331,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float bsum = 0.f;
         if (half + 2 * ci < chunks && n < nlim && !splitk) {
           if (p.bias) bsum += __half2float(p.bias[n]);
-          if (p.row_bias) bsum += __half2float(p.row_bias[(long long)img * p.row_bias_ld + n]);
+          if (p.row_bias && m_blk * kBM < p.M) bsum += __half2float(p.row_bias[(long long)img * p.row_bias_ld + n]);
         }
         sb[ci * 32 + lane] = bsum;
       }
@@ -301,10 +371,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c + 2 >= chunks) {  // last TMEM read of this warp for the tile: release the accumulator
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
+          if (lane == 0) {
+            if (TWO) bar_arrive_leader(&tmem_empty[acc]);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
+          }
         }
         const int n0 = n_blk * BN + c0;
         if (n0 >= nlim) continue;                 // warp-uniform
+        if (p.flags & 0x200u) continue;           // timing experiment only (tools/gemm_probe.py): epilogue math + stores skipped
         const bool full32 = n0 + 32 <= nlim;
         if (!(MODE == 0 && p.tma_store && full32) && !row_ok) continue;   // the TMA path needs the whole warp
         if constexpr (splitk) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
@@ -401,16 +475,20 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (half >= chunks) {  // this warp had no chunk in the tile (BN <= 32): still release it
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
+        if (lane == 0) {
+          if (TWO) bar_arrive_leader(&tmem_empty[acc]);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&tmem_empty[acc])) : "memory");
+        }
       }
     }
   }
   if (MODE == 0 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging reads + writes done
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();   // TWO: the peer may still signal this CTA's barriers / read its operands
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
   }
 }
 

@@ -1,6 +1,7 @@
 // Host side of include/gd_unet.h + the small fused kernels around the tcgen05 GEMM.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gd_gemm.cuh"
@@ -10,6 +11,7 @@
 namespace {
 thread_local char g_err[512] = {0};
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_pair_launches{0};   // GEMM launches that ran as CTA pairs (cta_group::2)
 
 int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -59,14 +61,23 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 // (griddepcontrol.launch_dependents) and waits for its predecessors' memory before touching global
 // data (griddepcontrol.wait), so launch latency and kernel prologues overlap the previous kernel.
 template <typename... KArgs, typename... Args>
-void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+void launch_pdl_cluster(int cluster_x, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cluster_x > 1) {   // thread-block cluster (CTA pair of the cta_group::2 GEMM)
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_pdl_cluster(1, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 #define LAUNCH_CHECK(what)              \
   do {                                  \
@@ -517,6 +528,7 @@ extern "C" {
 
 const char* gd_unet_last_error(void) { return g_err; }
 uint64_t gd_unet_launch_count(void) { return g_launches.load(); }
+uint64_t gd_unet_pair_launch_count(void) { return g_pair_launches.load(); }
 const char* gd_unet_version(void) { return "gd_unet 0.1 (sm_100a, tcgen05+TMA)"; }
 
 int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
@@ -563,6 +575,24 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   if (BN % 16 || BN < 16 || BN > 256 || ((a->flags & GD_EPI_GEGLU) && BN % 32))
     return fail(GD_UNET_ERR_INVALID_ARG, "gemm: block_n must be a multiple of 16 in 16..256");
 
+  // split-K (under-filled grids with long K) is decided first: it stays on the single-CTA kernel
+  int ksplit = 1;
+  const int num_kb_all = a->K / gdu::kBK;
+  const int m_tiles_all = (a->M + gdu::kBM - 1) / gdu::kBM, n_tiles_all = (a->N + BN - 1) / BN;
+  {
+    const long long tiles = (long long)m_tiles_all * n_tiles_all * a->batch;
+    const bool plain = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) && a->batch == 1 && a->N % 4 == 0 &&
+                       a->c_batch_stride == 0 && a->c_head_stride == 0;
+    if (plain && a->block_n <= 0 && tiles <= 74 && num_kb_all >= 24) {
+      int ks = (int)(148 / tiles);
+      if (ks > num_kb_all / 6) ks = num_kb_all / 6;
+      if (ks > 16) ks = 16;
+      if (ks >= 2 && (size_t)ks * a->M * a->N <= ((size_t)24 << 20)) ksplit = ks;
+    }
+  }
+  // CTA pairs (cta_group::2): every GEMM with at least two M tiles per batch entry
+  static const bool pair_enabled = []() { const char* e = getenv("GD_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  const bool two = pair_enabled && ksplit == 1 && m_tiles_all >= 2;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->a_dim[0], (cuuint64_t)a->a_dim[1], (cuuint64_t)a->a_dim[2], (cuuint64_t)a->a_dim[3]};
@@ -574,7 +604,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   {
     cuuint64_t dims[3] = {(cuuint64_t)a->b_dim[0], (cuuint64_t)a->b_dim[1], (cuuint64_t)a->b_dim[2]};
     cuuint64_t str[2] = {(cuuint64_t)a->b_stride[0], (cuuint64_t)a->b_stride[1]};
-    cuuint32_t box[3] = {(cuuint32_t)gdu::kBK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)gdu::kBK, (cuuint32_t)(two ? BN / 2 : BN), 1};   // a CTA of a pair stages half of the B tile
     const int rc = make_map(&tmB, a->B, 3, dims, str, box);
     if (rc != GD_UNET_OK) return rc;
   }
@@ -601,7 +631,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.row_bias_ld = a->row_bias_ld > 0 ? a->row_bias_ld : a->N;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
-  const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)BN * gdu::kBK * 2 + 1023) & ~(size_t)1023);
+  const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
   // one persistent CTA per SM owns the shared memory: operand ring + epilogue staging + barriers/bias
   const size_t smem_max = 227 * 1024, fixed = 1024 + 256 + 64 + gdu::kEpiWarps * 128 * sizeof(float);
   const bool mode0 = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED));
@@ -614,33 +644,23 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     stg_bufs = 1;
     stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
   }
-  if (stages > 8) stages = 8;
+  if (stages > 6) stages = 6;   // deeper rings measured no faster (profiles/r01_gemm_pair_stage_sweep.txt)
   if (stages < 2) stages = 2;
+  static const int stages_cap = []() { const char* e = getenv("GD_GEMM_STAGES"); return e ? atoi(e) : 0; }();   // tuning experiments
+  if (stages_cap >= 2 && stages > stages_cap) stages = stages_cap;
   p.stages = stages;
   p.stg_bufs = stg_bufs;
-  p.m_tiles = (a->M + gdu::kBM - 1) / gdu::kBM;
-  p.n_tiles = (a->N + BN - 1) / BN;
+  p.m_tiles = two ? (m_tiles_all + 1) / 2 : m_tiles_all;   // pairs of M tiles for the CTA-pair kernel
+  p.n_tiles = n_tiles_all;
   p.ksplit = 1; p.kb_per_split = p.num_kb; p.ws = nullptr;
-  // split-K for under-filled grids with long K (the 8x8 / 16x16 convolutions): partials in fp32,
-  // summed in a fixed order by k_splitk_finalize (deterministic)
+  // split-K partials in fp32, summed in a fixed order by k_splitk_finalize (deterministic)
   static float* ws = nullptr;
   const size_t ws_floats = (size_t)24 << 20;  // 96 MB
-  {
-    const long long tiles = (long long)p.m_tiles * p.n_tiles * a->batch;
-    const bool plain = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) && a->batch == 1 && a->N % 4 == 0 &&
-                       a->c_batch_stride == 0 && a->c_head_stride == 0;
-    if (plain && a->block_n <= 0 && tiles <= 74 && p.num_kb >= 24) {
-      int ks = (int)(148 / tiles);
-      if (ks > p.num_kb / 6) ks = p.num_kb / 6;
-      if (ks > 16) ks = 16;
-      if (ks >= 2 && (size_t)ks * a->M * a->N <= ws_floats) {
-        if (!ws && cudaMalloc(&ws, ws_floats * sizeof(float)) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "gemm: split-K workspace");
-        p.ksplit = ks;
-        p.kb_per_split = (p.num_kb + ks - 1) / ks;
-        p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
-        p.ws = ws;
-      }
-    }
+  if (ksplit > 1) {
+    if (!ws && cudaMalloc(&ws, ws_floats * sizeof(float)) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "gemm: split-K workspace");
+    p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
+    p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+    p.ws = ws;
   }
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
   const size_t smem = stages * stage_bytes + (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed;
@@ -662,17 +682,31 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(gdu::k_gemm_tcgen05<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    const int lim = 227 * 1024;
+    if (cudaFuncSetAttribute(gdu::k_gemm_tcgen05<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
       return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
   }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  if (p.ksplit > 1) launch_pdl(gdu::k_gemm_tcgen05<3>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
-  else if (a->flags & GD_EPI_GEGLU) launch_pdl(gdu::k_gemm_tcgen05<1>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
-  else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl(gdu::k_gemm_tcgen05<2>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
-  else launch_pdl(gdu::k_gemm_tcgen05<0>, dim3(grid), dim3(gdu::kGemmThreads), smem, stream, tmA, tmB, tmC, p);
+  const dim3 blk(gdu::kGemmThreads);
+  if (two) {
+    g_pair_launches.fetch_add(1, std::memory_order_relaxed);
+    const int pairs = num_sms / 2;
+    const dim3 grid(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
+    if (a->flags & GD_EPI_GEGLU) launch_pdl_cluster(2, gdu::k_gemm_tcgen05<1, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+    else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl_cluster(2, gdu::k_gemm_tcgen05<2, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+    else launch_pdl_cluster(2, gdu::k_gemm_tcgen05<0, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+  } else {
+    const dim3 grid(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    if (p.ksplit > 1) launch_pdl(gdu::k_gemm_tcgen05<3, false>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+    else if (a->flags & GD_EPI_GEGLU) launch_pdl(gdu::k_gemm_tcgen05<1, false>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+    else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl(gdu::k_gemm_tcgen05<2, false>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+    else launch_pdl(gdu::k_gemm_tcgen05<0, false>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+  }
   LAUNCH_CHECK("k_gemm_tcgen05");
   if (p.ksplit > 1) {
     const long long n4 = (long long)a->M * a->N / 4;
@@ -885,12 +919,12 @@ int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const voi
   if (y) {
     const int C8 = C / 8;
     if (256 % C8 == 0) {   // fast sweep: 4 loads in flight per thread
-      int pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 4);
+      int pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 2);
       const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
       if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
-      if (silu) launch_pdl(gdu::k_gn_apply_fast<true, 4>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
+      if (silu) launch_pdl(gdu::k_gn_apply_fast<true, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
                            (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
-      else launch_pdl(gdu::k_gn_apply_fast<false, 4>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
+      else launch_pdl(gdu::k_gn_apply_fast<false, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
                       (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
       LAUNCH_CHECK("k_gn_apply_fast");
       return GD_UNET_OK;
@@ -968,6 +1002,18 @@ int gd_vae_prep(const float* color, void* y, int B, int H, int W, float a, float
   const long long n = (long long)B * 4 * H * W;
   launch_pdl(gdu::k_vae_prep, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, color, (__half*)y, B, (long long)H * W, a, shift);
   LAUNCH_CHECK("k_vae_prep");
+  return GD_UNET_OK;
+}
+int gd_vae_im2col(const float* color, void* A, int B, int H, int W, float a, float shift, gd_ustream_t s) {
+  const long long n = (long long)B * H * W * 8;
+  launch_pdl(gdu::k_vae_im2col, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, color, (__half*)A, B, H, W, a, shift);
+  LAUNCH_CHECK("k_vae_im2col");
+  return GD_UNET_OK;
+}
+int gd_vae_dimg_gather(const void* Z, float* dcolor, int B, int H, int W, float scale, gd_ustream_t s) {
+  const long long n = (long long)B * H * W;
+  launch_pdl(gdu::k_vae_dimg_gather, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)Z, dcolor, B, H, W, scale);
+  LAUNCH_CHECK("k_vae_dimg_gather");
   return GD_UNET_OK;
 }
 int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling, gd_ustream_t s) {

@@ -206,10 +206,15 @@ k_gn_apply_fast(const __half* __restrict__ x, __half* __restrict__ y, const floa
   const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
   const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C) + ch;
   uint4* yb = reinterpret_cast<uint4*>(y + (size_t)n * HW * C) + ch;
-  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
-    uint4 v[U];
+  uint4 v[U], nx[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) if (pix + u * PP < p1) v[u] = xb[(size_t)(pix + u * PP) * C8];
+  for (int u = 0; u < U; u++) nx[u] = (p0 + pl + u * PP < p1) ? xb[(size_t)(p0 + pl + u * PP) * C8] : make_uint4(0, 0, 0, 0);
+  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = nx[u];
+    const int np = pix + PP * U;                       // prefetch the next iteration
+#pragma unroll
+    for (int u = 0; u < U; u++) if (np + u * PP < p1) nx[u] = xb[(size_t)(np + u * PP) * C8];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (pix + u * PP >= p1) break;
@@ -249,16 +254,22 @@ k_gn_bwd_apply_fast(const __half* __restrict__ x, const __half* dz, const __half
   const uint4* gb = reinterpret_cast<const uint4*>(dz + base) + ch;
   const uint4* ab = add ? reinterpret_cast<const uint4*>(add + base) + ch : nullptr;
   uint4* ob = reinterpret_cast<uint4*>(dx + base) + ch;
-  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
-    uint4 xv[U], gv[U], av[U];
+  uint4 xv[U], gv[U], av[U], nxv[U], ngv[U], nav[U];
+  auto fetch = [&](int pp, uint4 (&X)[U], uint4 (&G)[U], uint4 (&A)[U]) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const bool ok = pix + u * PP < p1;
-      const size_t o = (size_t)(pix + u * PP) * C8;
-      xv[u] = ok ? xb[o] : make_uint4(0, 0, 0, 0);
-      gv[u] = ok ? gb[o] : make_uint4(0, 0, 0, 0);
-      av[u] = (ok && ab) ? ab[o] : make_uint4(0, 0, 0, 0);
+      const bool ok = pp + u * PP < p1;
+      const size_t o = (size_t)(pp + u * PP) * C8;
+      X[u] = ok ? xb[o] : make_uint4(0, 0, 0, 0);
+      G[u] = ok ? gb[o] : make_uint4(0, 0, 0, 0);
+      A[u] = (ok && ab) ? ab[o] : make_uint4(0, 0, 0, 0);
     }
+  };
+  fetch(p0 + pl, nxv, ngv, nav);
+  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) { xv[u] = nxv[u]; gv[u] = ngv[u]; av[u] = nav[u]; }
+    fetch(pix + PP * U, nxv, ngv, nav);                // next iteration's loads in flight during the math
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (pix + u * PP >= p1) break;
@@ -422,6 +433,51 @@ __global__ void k_vae_dimg(const __half* __restrict__ dx, float* __restrict__ dc
   const float2 a = __half22float2(h[0]), c = __half22float2(h[1]);
   float* d = dcolor + (size_t)b * 3 * HW + p;
   d[0] = a.x * scale; d[HW] = a.y * scale; d[2 * HW] = c.x * scale;
+}
+
+// ---- conv_in as a GEMM: im2col of the 3-channel image, K = 27 taps padded to 64 -------------------
+// A[(b,y,x), (ky*3+kx)*3+c] = a*color[b,c,y+ky-1,x+kx-1] + sh (0 outside the image: the conv pads the
+// normalised image with zeros). One thread per pixel writes its 128-byte row.
+__global__ void __launch_bounds__(256)
+k_vae_im2col(const float* __restrict__ color, __half* __restrict__ A, int B, int H, int W, float a, float sh) {
+  pdl_entry();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, 16-byte chunk of its row)
+  const long long HW = (long long)H * W, i = t >> 3;
+  const int u = (int)(t & 7);
+  if (i >= (long long)B * HW) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / HW);
+  __align__(16) __half v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = u * 8 + j, tap = k / 3, c = k - tap * 3;
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    const bool ok = k < 27 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+    v[j] = __float2half_rn(ok ? a * color[((long long)b * 3 + c) * HW + (long long)yy * W + xx] + sh : 0.f);
+  }
+  reinterpret_cast<uint4*>(A)[t] = *reinterpret_cast<const uint4*>(v);
+}
+// ---- conv_in data gradient from the per-pixel tap products Z[(b,y,x), (ky*3+kx)*3+c] (fp16, 32 wide):
+// dcolor[b,c,y,x] = scale * sum_{ky,kx} Z[(b, y-ky+1, x-kx+1), (ky*3+kx)*3+c]
+__global__ void __launch_bounds__(256)
+k_vae_dimg_gather(const __half* __restrict__ Z, float* __restrict__ dcolor, int B, int H, int W, float scale) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W;
+  if (i >= (long long)B * HW) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / HW);
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+    for (int kx = 0; kx < 3; kx++) {
+      const int yy = y - ky + 1, xx = x - kx + 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __half* z = Z + (((long long)b * H + yy) * W + xx) * 32 + (ky * 3 + kx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[c] += __half2float(z[c]);
+    }
+  float* d = dcolor + (long long)b * 3 * HW + (long long)y * W + x;
+  d[0] = acc[0] * scale; d[HW] = acc[1] * scale; d[2 * HW] = acc[2] * scale;
 }
 
 }  // namespace gdu

@@ -49,6 +49,7 @@ def lib():
         L.gd_unet_last_error.restype = ctypes.c_char_p
         L.gd_unet_version.restype = ctypes.c_char_p
         L.gd_unet_launch_count.restype = ctypes.c_uint64
+        L.gd_unet_pair_launch_count.restype = ctypes.c_uint64
         L.gd_unet_gemm.argtypes = [ctypes.POINTER(GdGemmArgs), ctypes.c_void_p]
         vp, i, f, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
         L.gd_unet_flash_attn.argtypes = [vp, vp, vp, vp, i, i, i, i, ll, ll, ll, ll, f, vp]
@@ -79,7 +80,9 @@ def lib():
         L.gd_vae_dimg.argtypes = [vp, vp, i, i, i, i, f, vp]
         for name in ("groupnorm_stats", "groupnorm_bwd", "softmax_bwd", "transpose", "depth_to_space"):
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
-        for name in ("prep", "sample", "sample_bwd", "dimg"):
+        L.gd_vae_im2col.argtypes = [vp, vp, i, i, i, f, f, vp]
+        L.gd_vae_dimg_gather.argtypes = [vp, vp, i, i, i, f, vp]
+        for name in ("prep", "sample", "sample_bwd", "dimg", "im2col", "dimg_gather"):
             getattr(L, "gd_vae_" + name).restype = ctypes.c_int
         for name in ("gemm", "flash_attn", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
                      "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad",

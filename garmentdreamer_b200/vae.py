@@ -42,14 +42,15 @@ class VAEEncoderB200:
         for k, v in sd.items():
             if v.dim() == 1:
                 self.w[k] = h(v)
-        # conv_in: [128,3,3,3] -> [128,3,3,4] (4th input channel is zero padding)
-        w = sd["encoder.conv_in.weight"]
-        w4 = torch.zeros(w.shape[0], 3, 3, 4, device=self.device)
-        w4[..., :3] = w.permute(0, 2, 3, 1)
-        self.w["conv_in.fwd"] = h(w4)
-        wt = torch.zeros(16, 3, 3, w.shape[0], device=self.device)          # dgrad: 3 real outputs of 16
-        wt[:3] = w.flip(2, 3).permute(1, 2, 3, 0)
-        self.w["conv_in.bwd"] = h(wt.reshape(16, -1))
+        # conv_in as a GEMM over im2col rows: K index (ky*3+kx)*3+c, 27 real columns of 64
+        w = sd["encoder.conv_in.weight"]                                      # [128,3,3,3] = [co,c,ky,kx]
+        wf = torch.zeros(w.shape[0], 64, device=self.device)
+        wf[:, :27] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 27)
+        self.w["conv_in.fwd"] = h(wf)
+        # data gradient: Z[p, (ky,kx,c)] = dY[p,:] . w[:,c,ky,kx]  (27 real rows of 32), then a 9-tap gather
+        wz = torch.zeros(32, w.shape[0], device=self.device)
+        wz[:27] = w.permute(2, 3, 1, 0).reshape(27, w.shape[0])
+        self.w["conv_in.bwd"] = h(wz)
         for k in [k for k in sd if k.endswith(".weight") and sd[k].dim() == 4 and k != "encoder.conv_in.weight"]:
             base, v = k[:-len(".weight")], sd[k]
             if base in ("encoder.conv_out", "quant_conv"):
@@ -180,10 +181,10 @@ class VAEEncoderB200:
         imgs = imgs.detach().float().contiguous()
         noise = noise.detach().float().contiguous()
         a, sh = (2.0, -1.0) if input_range == "01" else (1.0, 0.0)
-        x4 = torch.empty((B, 4, H, W), dtype=torch.float16, device=imgs.device)
-        ops._chk(L.gd_vae_prep(imgs.data_ptr(), x4.data_ptr(), B, H, W, a, sh, st), "vae_prep")
+        cols = torch.empty((B * H * W, 64), dtype=torch.float16, device=imgs.device)
+        ops._chk(L.gd_vae_im2col(imgs.data_ptr(), cols.data_ptr(), B, H, W, a, sh, st), "vae_im2col")
         saved = []
-        x = ops.conv_in(x4, self.w["conv_in.fwd"], self.w["encoder.conv_in.bias"])
+        x = ops.linear(cols, self.w["conv_in.fwd"], self.w["encoder.conv_in.bias"]).view(B, H, W, -1)
         for i in range(4):
             for j in range(2):
                 x = self._resnet_fwd(f"encoder.down_blocks.{i}.resnets.{j}", x, saved)
@@ -222,9 +223,9 @@ class VAEEncoderB200:
                 d = self._attn_bwd(rec, d)
             else:
                 d = self._down_bwd(rec, d)
-        dx16 = ops.conv3x3(d, self.w["conv_in.bwd"])                              # [B,H,W,16], 3 real channels
+        z = ops.linear(d.view(B * H * W, -1), self.w["conv_in.bwd"])              # [B*H*W,32] per-pixel tap products
         dimg = torch.empty((B, 3, H, W), dtype=torch.float32, device=g.device)
-        ops._chk(L.gd_vae_dimg(dx16.data_ptr(), dimg.data_ptr(), B, H, W, 16, a / GRAD_SCALE, st), "vae_dimg")
+        ops._chk(L.gd_vae_dimg_gather(z.data_ptr(), dimg.data_ptr(), B, H, W, a / GRAD_SCALE, st), "vae_dimg_gather")
         return dimg
 
     # ---- autograd + the diffusers surface the reference calls ---------------------------------

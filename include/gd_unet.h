@@ -151,6 +151,14 @@ int gd_unet_depth_to_space(const void* x, void* y, int N, int H, int W, int C, g
    ((a, shift) = (2, -1) for images in [0,1], the `imgs * 2 - 1` of encode_images). */
 int gd_vae_prep(const float* color_nchw, void* y, int B, int H, int W, float a, float shift,
                 gd_ustream_t stream);
+/* conv_in (3 -> C, 3x3, pad 1) as a GEMM: im2col rows A fp16 [B*H*W, 64], column (ky*3+kx)*3+c =
+   a*color[b,c,y+ky-1,x+kx-1]+shift (0 outside the image; columns 27..63 zero). */
+int gd_vae_im2col(const float* color_nchw, void* A, int B, int H, int W, float a, float shift,
+                  gd_ustream_t stream);
+/* Its data gradient from the per-pixel tap products Z fp16 [B*H*W, 32] (column (ky*3+kx)*3+c):
+   dcolor[b,c,y,x] = scale * sum_taps Z[(b, y-ky+1, x-kx+1), (ky*3+kx)*3+c]; fp32 NCHW out. */
+int gd_vae_dimg_gather(const void* Z, float* dcolor_nchw, int B, int H, int W, float scale,
+                       gd_ustream_t stream);
 /* DiagonalGaussianDistribution.sample() * scaling: moments fp16 NHWC [B,hw,8] (mean | logvar,
    logvar clamped to [-30,20]), noise fp32 NCHW [B,4,hw] -> latents fp32 NCHW [B,4,hw]. */
 int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling,
@@ -174,6 +182,8 @@ int gd_unet_pool_latents_bwd(const float* grad, const float* mix, float* dcolor_
 
 const char* gd_unet_last_error(void);
 uint64_t gd_unet_launch_count(void);
+/* GEMM launches so far that ran as CTA pairs (tcgen05 cta_group::2, clusters of 2). */
+uint64_t gd_unet_pair_launch_count(void);
 const char* gd_unet_version(void);
 
 #ifdef __cplusplus
