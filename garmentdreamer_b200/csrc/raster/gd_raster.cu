@@ -1,11 +1,13 @@
 // Host side of the C ABI declared in include/gd_raster.h (unity build of the kernel files).
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
 #include "gd_raster_common.cuh"
 #include "gd_raster_forward.cu"
 #include "gd_raster_backward.cu"
+#include "gd_params.cu"
 
 namespace {
 thread_local char g_err[512] = {0};
@@ -201,6 +203,54 @@ int gd_mark_visible(int P, const float* means3D, const float* viewmatrix, const 
   gd::k_mark_visible<<<(P + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       P, means3D, viewmatrix, present);
   GD_LAUNCH_CHECK("k_mark_visible");
+  return GD_OK;
+}
+
+// ---- fused parameter kernels (include/gd_raster.h, "Gaussian parameters" section) --------------
+int gd_params_activate(int P, const float* xyz, const float* f_dc, const float* opacity, const float* scaling,
+                       const float* rotation, float* packed_out, gd_stream_t stream) {
+  if (P < 0 || (P > 0 && (!xyz || !f_dc || !opacity || !scaling || !rotation || !packed_out)))
+    return fail(GD_ERR_INVALID_ARG, "params_activate: null pointer%s");
+  if (P == 0) return GD_OK;
+  gd::k_params_activate<<<(P + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, xyz, f_dc, opacity, scaling, rotation, packed_out);
+  GD_LAUNCH_CHECK("k_params_activate");
+  return GD_OK;
+}
+int gd_params_adam(int P, float* xyz, float* f_dc, float* opacity, float* scaling, float* rotation, const float* packed_grad,
+                   float* exp_avg, float* exp_avg_sq, const float* lr5, float beta1, float beta2, float eps, int step,
+                   gd_stream_t stream) {
+  if (P < 0 || step < 1 || !lr5 || (P > 0 && (!xyz || !f_dc || !opacity || !scaling || !rotation || !packed_grad || !exp_avg || !exp_avg_sq)))
+    return fail(GD_ERR_INVALID_ARG, "params_adam: null pointer or step < 1%s");
+  if (P == 0) return GD_OK;
+  gd::AdamHyper h;
+  for (int k = 0; k < 5; k++) h.lr[k] = lr5[k];
+  h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
+  h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  h.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  gd::k_params_adam<<<(P + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, xyz, f_dc, opacity, scaling, rotation, packed_grad,
+                                                                                         exp_avg, exp_avg_sq, h);
+  GD_LAUNCH_CHECK("k_params_adam");
+  return GD_OK;
+}
+int gd_densify_stats(int P, int B, const float* dmeans2D_sum, const int* radii, float* xyz_gradient_accum, float* denom,
+                     float* max_radii2D, gd_stream_t stream) {
+  if (P < 0 || B < 1 || (P > 0 && (!dmeans2D_sum || !radii || !xyz_gradient_accum || !denom || !max_radii2D)))
+    return fail(GD_ERR_INVALID_ARG, "densify_stats: null pointer%s");
+  if (P == 0) return GD_OK;
+  gd::k_densify_stats<<<(P + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, B, dmeans2D_sum, radii, xyz_gradient_accum, denom, max_radii2D);
+  GD_LAUNCH_CHECK("k_densify_stats");
+  return GD_OK;
+}
+
+int gd_cameras_from_c2w(int B, const float* c2w, const float* tan_half_fovx, const float* tan_half_fovy, float znear, float zfar,
+                        float* out35, gd_stream_t stream) {
+  if (B < 1 || B > GD_MAX_VIEWS) return fail(GD_ERR_INVALID_ARG, "cameras_from_c2w: B must be in 1..GD_MAX_VIEWS%s");
+  if (!c2w || !tan_half_fovx || !tan_half_fovy || !out35) return fail(GD_ERR_INVALID_ARG, "cameras_from_c2w: null pointer%s");
+  gd::CamIntrinsics in;
+  for (int b = 0; b < B; b++) { in.tan_half_fovx[b] = tan_half_fovx[b]; in.tan_half_fovy[b] = tan_half_fovy[b]; }
+  in.znear = znear; in.zfar = zfar;
+  gd::k_cameras_from_c2w<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(B, c2w, in, out35);
+  GD_LAUNCH_CHECK("k_cameras_from_c2w");
   return GD_OK;
 }
 

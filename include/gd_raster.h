@@ -166,6 +166,34 @@ int gd_raster_backward(const GdBwdArgs* args, gd_stream_t stream);
 int gd_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     uint8_t* present, gd_stream_t stream);
 
+/* ---- Gaussian parameters: fused activation / optimiser / statistics kernels ----
+ * Packed struct-of-arrays layout of the ACTIVATED parameters and of their gradient, 14 floats per
+ * Gaussian in one buffer:  xyz 3P | f_dc 3P | opacity P | scales 3P | rotation 4P.
+ * gd_params_activate replaces get_xyz/get_features/get_opacity/get_scaling/get_rotation
+ *   (GS/scene/gaussian_model.py:95-115: identity, identity, sigmoid, exp, F.normalize), which the
+ *   reference re-evaluates per view (GS/gaussian_renderer/__init__.py:53-80).
+ * gd_params_adam replaces autograd through those activations + torch.optim.Adam(eps=1e-15) over the
+ *   parameter groups of gaussian_model.py:156-165 (lr5 = xyz, f_dc, opacity, scaling, rotation;
+ *   step = 1-based optimiser step): RAW parameters and exp_avg / exp_avg_sq [14P] updated in place.
+ * gd_densify_stats replaces add_densification_stats (:415-419) and the max_radii2D update of
+ *   TS/systems/GaussianDreamer.py:269-275 for a batch of B views (radii i32 [B,P]). */
+int gd_params_activate(int P, const float* xyz, const float* f_dc, const float* opacity, const float* scaling,
+                       const float* rotation, float* packed_out, gd_stream_t stream);
+int gd_params_adam(int P, float* xyz, float* f_dc, float* opacity, float* scaling, float* rotation,
+                   const float* packed_grad, float* exp_avg, float* exp_avg_sq, const float* lr5,
+                   float beta1, float beta2, float eps, int step, gd_stream_t stream);
+int gd_densify_stats(int P, int B, const float* dmeans2D_sum, const int* radii, float* xyz_gradient_accum,
+                     float* denom, float* max_radii2D, gd_stream_t stream);
+
+/* Batched camera construction: replaces Camera.__init__ (GS/scene/cameras.py:50-53,
+ * GS/utils/graphics_utils.py:59-101), which the reference runs on the CPU per view per iteration.
+ * c2w: DEVICE fp32 [B,4,4] row-major camera-to-world (batch['c2w_3dgs']); tan_half_fovx/y: HOST
+ * arrays [B] (the caller needs them on the host anyway for GdView); out35: DEVICE fp32 [B,35] =
+ * world_view_transform 16 | full_proj_transform 16 | camera_center 3, in the transposed
+ * (row-vector) convention GdView expects. */
+int gd_cameras_from_c2w(int B, const float* c2w, const float* tan_half_fovx, const float* tan_half_fovy,
+                        float znear, float zfar, float* out35, gd_stream_t stream);
+
 const char* gd_last_error(void);
 /* Number of kernels this library has launched so far in this process (bench.py gpu_launches). */
 uint64_t gd_launch_count(void);
