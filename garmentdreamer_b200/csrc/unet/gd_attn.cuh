@@ -32,6 +32,17 @@ __device__ __forceinline__ void bar_arrive(uint64_t* b) {
 __device__ __forceinline__ uint32_t umma_idesc_f16_n(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -94,7 +105,7 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const uint32_t tmem_S0 = tmem, tmem_O = tmem + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       bar_expect_tx(q_full, kQBytes);
       tma_load_3d(sQ, &tmQ, q_full, h * 64, m_blk * 128, b);
       for (int i = 0; i < iters; i++) {
@@ -119,7 +130,7 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       bar_wait(&k_full[s], (i >> 1) & 1);
       bar_wait(&s_empty[s], ((i >> 1) & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t da = umma_desc_sw128(s2u(sQ)), db = umma_desc_sw128(s2u(sK + s * kKBytes));
 #pragma unroll
         for (int k = 0; k < 4; k++) umma_f16(tmem_S0 + s * 128, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
@@ -136,7 +147,7 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         bar_wait(&p_full[vs], (vi >> 1) & 1);
         bar_wait(&v_full[vs], (vi >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < 2; kb++) {
             const uint64_t da = umma_desc_sw128(s2u(sP + vs * kPBytes + kb * 128 * 64 * 2));
@@ -167,13 +178,21 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (i < n) {
         // ---- pass 1: row maximum over this warp's 64 keys ----
+        uint32_t va[32], vb[32];
+        tmem_ld32_issue(tmem_S0 + s * 128 + lane_base + hb * 64, va);
+        tmem_ld32_issue(tmem_S0 + s * 128 + lane_base + hb * 64 + 32, vb);
+        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S0 + s * 128 + lane_base + hb * 64 + c * 32, v);
-          if (kmax >= 64) {
+          uint32_t (&v)[32] = c == 0 ? va : vb;
+          if (kmax >= 64) {   // four independent chains instead of one 32-deep FMNMX dependency chain
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-            for (int t = 0; t < 32; t++) m = fmaxf(m, __uint_as_float(v[t]));
+            for (int t = 4; t < 32; t += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[t])); m1 = fmaxf(m1, __uint_as_float(v[t + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[t + 2])); m3 = fmaxf(m3, __uint_as_float(v[t + 3]));
+            }
+            m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
           } else {
 #pragma unroll
             for (int t = 0; t < 32; t++)
@@ -194,15 +213,17 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         bar_wait(&p_empty[ps], ((vi >> 1) & 1) ^ 1);
         const float mc = m * p.scale_log2e;
         uint8_t* blk = sP + ps * kPBytes + hb * (128 * 64 * 2) + r * 128;
+        uint32_t va[32], vb[32];       // both 32-key chunks in flight, one wait, then the S buffer is free
+        tmem_ld32_issue(tmem_S0 + s * 128 + lane_base + hb * 64, va);
+        tmem_ld32_issue(tmem_S0 + s * 128 + lane_base + hb * 64 + 32, vb);
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(&s_empty[s]);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S0 + s * 128 + lane_base + hb * 64 + c * 32, v);
-          if (c == 1) {  // all TMEM reads of this S buffer by this warp are done
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) bar_arrive(&s_empty[s]);
-          }
+          uint32_t (&v)[32] = c == 0 ? va : vb;
+          float lp[4] = {0.f, 0.f, 0.f, 0.f};                 // independent partial row sums (no 64-deep FADD chain)
 #pragma unroll
           for (int g = 0; g < 4; g++) {                       // 4 chunks of 8 keys = 16 bytes
             __align__(16) __half2 hv[4];
@@ -216,12 +237,13 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
                 if (k0 >= kmax) e0 = 0.f;
                 if (k0 + 1 >= kmax) e1 = 0.f;
               }
-              l += e0 + e1;
+              lp[t] += e0 + e1;
               hv[t] = __floats2half2_rn(e0, e1);
             }
             const int chunk = c * 4 + g;                       // 16-byte chunk index in the 128 B row
             *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(hv);
           }
+          l += (lp[0] + lp[1]) + (lp[2] + lp[3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
         __syncwarp();

@@ -55,6 +55,14 @@ struct GemmKParams {
 __device__ __forceinline__ uint32_t s2u(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One elected lane of a converged warp. Unlike `lane == 0`, ptxas knows exactly one thread is active
+// behind this predicate, so operands of the async-unit instructions (UTCHMMA / UTMALDG / UTCBAR need
+// uniform registers) are moved with a single R2UR instead of a per-instruction broadcast loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(n));
 }
@@ -210,7 +218,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();  // everything above overlapped the previous kernel; its results are visible from here on
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer ----------------
       int it = 0;  // ring position, runs across tiles
       for (int t = tile0; t < total; t += tile_step) {
@@ -277,7 +285,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = it % S;
         bar_wait(&full[s], (it / S) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
           if (TWO) {
@@ -441,7 +449,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // registers -> swizzled staging tile -> one bulk tensor store per chunk (coalesced, async;
               // rows beyond M are clipped by the tensor map)
               uint8_t* stg = stg_base + (p.stg_bufs == 2 ? (st_cnt & 1u) * 2048 : 0u);
-              if (lane == 0) {   // the buffer's previous store has finished reading it
+              const bool leader = elect_one();   // bulk groups are per thread: the same elected lane issues and waits
+              if (leader) {   // the buffer's previous store has finished reading it
                 if (p.stg_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
               }
@@ -451,7 +460,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o[u];
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               __syncwarp();
-              if (lane == 0) {
+              if (leader) {
                 tma_store_4d(&tmC, stg, n0, m_blk * kBM + q * 32, zh, zb);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
@@ -482,7 +491,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  if (MODE == 0 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging reads + writes done
+  if (MODE == 0 && warp >= 2) {
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging reads + writes done
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (TWO) cluster_sync_all(); else __syncthreads();   // TWO: the peer may still signal this CTA's barriers / read its operands
   if (warp == 1) {
