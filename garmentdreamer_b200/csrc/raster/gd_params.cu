@@ -28,7 +28,8 @@ k_params_activate(int P, const float* __restrict__ xyz, const float* __restrict_
   o_op[i] = 1.0f / (1.0f + expf(-opacity[i]));                                   // torch.sigmoid
   const float4 q = *reinterpret_cast<const float4*>(rotation + 4 * (size_t)i);
   const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);   // F.normalize(eps=1e-12)
-  *reinterpret_cast<float4*>(o_rot + 4 * (size_t)i) = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+  float* r = o_rot + 4 * (size_t)i;   // the packed slice starts at float 10P: only 8-byte aligned in general
+  r[0] = q.x / n; r[1] = q.y / n; r[2] = q.z / n; r[3] = q.w / n;
 }
 
 struct AdamHyper {
@@ -68,7 +69,8 @@ k_params_adam(int P, float* __restrict__ xyz, float* __restrict__ f_dc, float* _
   }
   {
     const float4 q = *reinterpret_cast<const float4*>(rotation + 4 * (size_t)i);
-    const float4 g = *reinterpret_cast<const float4*>(grad + o_rot + 4 * (size_t)i);
+    const float* gp = grad + o_rot + 4 * (size_t)i;
+    const float4 g = make_float4(gp[0], gp[1], gp[2], gp[3]);
     const float nrm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
     const float n = fmaxf(nrm, 1e-12f);
     const float qx = q.x / n, qy = q.y / n, qz = q.z / n, qw = q.w / n;

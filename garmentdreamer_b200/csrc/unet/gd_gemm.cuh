@@ -388,7 +388,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n0 >= nlim) continue;                 // warp-uniform
         if (p.flags & 0x200u) continue;           // timing experiment only (tools/gemm_probe.py): epilogue math + stores skipped
         const bool full32 = n0 + 32 <= nlim;
-        if (!(MODE == 0 && p.tma_store && full32) && !row_ok) continue;   // the TMA path needs the whole warp
+        if (!(MODE == 0 && p.tma_store && full32) && !row_ok) continue;   // the staged paths need the whole warp
         if constexpr (splitk) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
           float* wdst = p.ws + ((size_t)ks * p.M + row) * p.N + n0;
           if (full32) {
@@ -445,7 +445,26 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               o[u] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                                 *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
             }
-            if (p.tma_store) {
+            if (p.tma_store == 2) {
+              // registers -> swizzled staging tile -> coalesced 16-byte stores: 4 lanes per 64-byte row
+              // segment, 8 rows per instruction (every 32-byte sector written whole). Synchronous, so
+              // the epilogue never queues behind the operand loads in the TMA unit.
+              uint8_t* stg = stg_base;
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 4; u++)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o[u];
+              __syncwarp();
+              const int piece = lane & 3;
+              const int row0 = m_blk * kBM + q * 32;
+#pragma unroll
+              for (int it = 0; it < 4; it++) {
+                const int r = it * 8 + (lane >> 2);
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
+                if (row0 + r < p.M)
+                  *reinterpret_cast<uint4*>(p.C + coff + (long long)(row0 + r) * p.ldc + n0 + piece * 8) = val;
+              }
+            } else if (p.tma_store == 1) {
               // registers -> swizzled staging tile -> one bulk tensor store per chunk (coalesced, async;
               // rows beyond M are clipped by the tensor map)
               uint8_t* stg = stg_base + (p.stg_bufs == 2 ? (st_cnt & 1u) * 2048 : 0u);

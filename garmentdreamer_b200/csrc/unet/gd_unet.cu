@@ -675,7 +675,9 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     cuuint32_t box[4] = {32, 32, 1, 1};
     const int rc = make_map(&tmC, a->C, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != GD_UNET_OK) return rc;
-    p.tma_store = 1;
+    // 2 = staged + coalesced st.global (default); 1 = staged + TMA store (GD_GEMM_TMA_STORE=1)
+    static const bool use_tma_store = []() { const char* e = getenv("GD_GEMM_TMA_STORE"); return e && e[0] == '1'; }();
+    p.tma_store = use_tma_store ? 1 : 2;
   }
   static int num_sms = 0;
   if (!num_sms) {

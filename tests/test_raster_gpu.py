@@ -159,12 +159,13 @@ def test_arena_overflow_regrows():
     assert torch.equal(col2, cases.ours_run(c, backward=False)["color"])
 
 
-def test_full_size_properties_c2():
-    """BASELINE config 2 size: 100k Gaussians, 4 views 512^2 -- properties that need no oracle."""
+@pytest.mark.parametrize("P,B,S", [(100000, 4, 512), (50000, 1, 1024), (500000, 8, 1024)], ids=["c2", "c4a", "c5"])
+def test_full_size_properties(P, B, S):
+    """BASELINE configs at full size (c2: 100k Gaussians, 4 views 512^2; c4a: 50k, one 1024^2 view;
+    c5: 500k, 8 views 1024^2) -- size-independent properties that need no oracle."""
     from garmentdreamer_b200 import raster
     from garmentdreamer_b200.synthetic import garment, sample_cameras
     dev = torch.device("cuda:0")
-    P, B, S = 100000, 4, 512
     g = {k: v.to(dev) for k, v in garment(P, 0).items()}
     views = [raster.View(c.viewmatrix.to(dev), c.projmatrix.to(dev), c.campos.to(dev), c.tanfovx, c.tanfovy)
              for c in sample_cameras(B, S, S)]
