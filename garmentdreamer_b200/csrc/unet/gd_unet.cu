@@ -722,9 +722,15 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
 
 int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq, int Tk,
                        long long ldq, long long ldk, long long ldv, long long ldo, float scale, gd_ustream_t stream_) {
+  return gd_unet_flash_attn_ex(q, k, vt, out, B, heads, Tq, Tk, ldq, ldk, ldv, ldo, 0, scale, stream_);
+}
+int gd_unet_flash_attn_ex(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq, int Tk,
+                          long long ldq, long long ldk, long long ldv, long long ldo, long long v_batch_stride, float scale,
+                          gd_ustream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!q || !k || !vt || !out || B < 1 || heads < 1 || Tq < 1 || Tk < 1) return fail(GD_UNET_ERR_INVALID_ARG, "flash_attn: bad argument");
-  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return fail(GD_UNET_ERR_INVALID_ARG, "flash_attn: leading dims must be multiples of 8");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || (v_batch_stride % 8))
+    return fail(GD_UNET_ERR_INVALID_ARG, "flash_attn: leading dims must be multiples of 8");
   const int C = heads * 64;
   CUtensorMap tmQ, tmK, tmV;
   {
@@ -738,7 +744,7 @@ int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, 
     rc = make_map(&tmK, k, 3, dk, sk, box);
     if (rc != GD_UNET_OK) return rc;
     cuuint64_t dv[3] = {(cuuint64_t)Tk, (cuuint64_t)C, (cuuint64_t)B};
-    cuuint64_t sv[2] = {(cuuint64_t)ldv * 2, (cuuint64_t)C * ldv * 2};
+    cuuint64_t sv[2] = {(cuuint64_t)ldv * 2, (cuuint64_t)(v_batch_stride > 0 ? v_batch_stride : C * ldv) * 2};
     cuuint32_t boxv[3] = {64, 64, 1};
     rc = make_map(&tmV, vt, 3, dv, sv, boxv);
     if (rc != GD_UNET_OK) return rc;

@@ -49,6 +49,17 @@ class UNetB200:
         for k in [k for k in self.w if k.endswith(".attn1.to_q.weight")]:
             base = k[:-len(".to_q.weight")]
             self.w[base + ".to_qk.weight"] = torch.cat([self.w[base + ".to_q.weight"], self.w[base + ".to_k.weight"]]).contiguous()
+        # cross-attention: the text K / V projections of all 16 layers share their input (the prompt
+        # embedding) -> one [sum C, 1024] GEMM each per forward instead of 32 small launches
+        names = [k[:-len(".to_k.weight")] for k in self.w if k.endswith(".attn2.to_k.weight")]
+        self._kv_off, off = {}, 0
+        for nme in names:
+            c = self.w[nme + ".to_k.weight"].shape[0]
+            self._kv_off[nme] = (off, c)
+            off += c
+        self._ctx_wk = torch.cat([self.w[nme + ".to_k.weight"] for nme in names]).contiguous()
+        self._ctx_wv = torch.cat([self.w[nme + ".to_v.weight"] for nme in names]).contiguous()
+        self._ctx_kv = None
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = 0
@@ -100,10 +111,12 @@ class UNetB200:
         if ctx is xn:  # self-attention: fused q|k projection, read through strided views
             qk = ops.linear(xn, w[p + ".to_qk.weight"])
             q, k = qk[:, :, :C], qk[:, :, C:]
-        else:
+            vt = ops.linear_transposed(ctx, w[p + ".to_v.weight"], (Tk + 7) // 8 * 8)
+        else:   # text keys / values: slices of the batched projections made once per forward
             q = ops.linear(xn, w[p + ".to_q.weight"])
-            k = ops.linear(ctx, w[p + ".to_k.weight"])
-        vt = ops.linear_transposed(ctx, w[p + ".to_v.weight"], (Tk + 7) // 8 * 8)
+            off, c = self._kv_off[p]
+            k_all, vt_all = self._ctx_kv
+            k, vt = k_all[:, :, off:off + c], vt_all[:, off:off + c, :]
         o = ops.flash_attention(q, k, vt, heads, Tk, 0.125)  # scores never leave TMEM / smem
         return ops.linear(o, w[p + ".to_out.0.weight"], w[p + ".to_out.0.bias"], residual=resid)
 
@@ -132,6 +145,8 @@ class UNetB200:
         # every consumer (ResnetBlock2D.time_emb_proj) applies SiLU first: do it once here
         emb = ops.small_linear(emb, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"], silu_out=True)
         emb = ops.small_linear(emb, self._temb_w, self._temb_b)   # every time_emb_proj at once
+        Tk = ctx.shape[1]
+        self._ctx_kv = (ops.linear(ctx, self._ctx_wk), ops.linear_transposed(ctx, self._ctx_wv, (Tk + 7) // 8 * 8))
         skips = [x]
         for i in range(4):
             for j in range(2):

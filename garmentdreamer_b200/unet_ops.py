@@ -53,6 +53,8 @@ def lib():
         L.gd_unet_gemm.argtypes = [ctypes.POINTER(GdGemmArgs), ctypes.c_void_p]
         vp, i, f, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
         L.gd_unet_flash_attn.argtypes = [vp, vp, vp, vp, i, i, i, i, ll, ll, ll, ll, f, vp]
+        L.gd_unet_flash_attn_ex.argtypes = [vp, vp, vp, vp, i, i, i, i, ll, ll, ll, ll, ll, f, vp]
+        L.gd_unet_flash_attn_ex.restype = ctypes.c_int
         L.gd_unet_groupnorm.argtypes = [vp, vp, vp, vp, i, i, i, i, f, i, vp]
         L.gd_unet_layernorm.argtypes = [vp, vp, vp, vp, i, i, f, vp]
         L.gd_unet_softmax.argtypes = [vp, ll, i, ll, vp]
@@ -315,8 +317,9 @@ def flash_attention(q, k, vt, heads, Tk, scale=0.125, out=None):
     B, Tq, C = q.shape[0], q.shape[1], heads * 64
     if out is None:
         out = torch.empty((B, Tq, C), dtype=torch.float16, device=q.device)
-    _chk(lib().gd_unet_flash_attn(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Tq, Tk,
-                                  q.stride(1), k.stride(1), vt.stride(1), out.stride(1), scale, _stream()), "flash_attn")
+    _chk(lib().gd_unet_flash_attn_ex(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Tq, Tk,
+                                     q.stride(1), k.stride(1), vt.stride(1), out.stride(1), vt.stride(0), scale, _stream()),
+         "flash_attn")
     return out
 
 

@@ -80,6 +80,11 @@ int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
 int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq,
                        int Tk, long long ldq, long long ldk, long long ldv, long long ldo, float scale,
                        gd_ustream_t stream);
+/* Same with an explicit batch stride (elements) of vt, for V^T slices of a wider [B, sum C, ldv]
+   tensor (all cross-attention V projections of the text computed by one GEMM); 0 = heads*64*ldv. */
+int gd_unet_flash_attn_ex(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq,
+                          int Tk, long long ldq, long long ldk, long long ldv, long long ldo,
+                          long long v_batch_stride, float scale, gd_ustream_t stream);
 
 /* GroupNorm over NHWC fp16 (+ optional SiLU). x,y: [N, HW, C]; gamma,beta fp16 [C]. */
 int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int N, int HW,
