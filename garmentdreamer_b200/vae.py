@@ -243,10 +243,13 @@ class _EncodeFn(torch.autograd.Function):
     def forward(ctx, imgs, noise, enc, input_range, scaling):
         ctx.enc = enc
         ctx.in_dtype = imgs.dtype
-        return enc.encode(imgs, noise, keep_for_backward=True, input_range=input_range, scaling=scaling)
+        lat = enc.encode(imgs, noise, keep_for_backward=True, input_range=input_range, scaling=scaling)
+        ctx.saved, enc._saved = enc._saved, None   # the graph node owns its activations (several encodes may be alive)
+        return lat
 
     @staticmethod
     def backward(ctx, grad_latents):
+        ctx.enc._saved, ctx.saved = ctx.saved, None
         return ctx.enc.backward(grad_latents).to(ctx.in_dtype), None, None, None, None
 
 
