@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def rel(a, b):
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
@@ -148,10 +148,14 @@ def test_autograd_and_diffusers_surface(vae):
     imgs = (xr2 * 2.0 - 1.0).half()
     lat2 = view.encode(imgs).latent_dist.sample(generator=g) * view.config.scaling_factor
     noise = torch.randn((1, 4, 16, 16), device="cuda", dtype=torch.float32, generator=torch.Generator(device="cuda").manual_seed(3))
-    ref = enc.encode(x, noise, keep_for_backward=False)
-    assert rel(lat2.float(), ref) < 2e-3          # fp16 rounding of the pm1 image and of the sample
+    ref = enc.encode(x, noise)
+    g_ref = enc.backward(gl)
+    e_lat = rel(lat2.float(), ref)
     lat2.float().backward(gl)
-    assert rel(xr2.grad, xr.grad) < 0.5 and torch.isfinite(xr2.grad).all()   # different noise draw: same scale, finite
+    e_grad = rel(xr2.grad, g_ref)
+    print(f"diffusers surface: latents {e_lat:.3e}, d/dimage {e_grad:.3e} vs the fused entry point (same noise)")
+    assert e_lat < 5e-3          # fp16 rounding of the [-1,1] image and of the sample before the scaling
+    assert e_grad < 2e-2 and torch.isfinite(xr2.grad).all()
 
 
 def test_guidance_call_differentiates_through_native_vae(vae):
