@@ -76,6 +76,7 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   __shared__ __align__(16) float s_part[2][kBwdChunk][kTilePix / 32][kGradF];
   __shared__ __align__(8) uint64_t s_bar[kBwdStages];
   __shared__ int s_max[kTilePix / 32];
+  __shared__ uint8_t s_mask[3][kBwdChunk];   // per record: warps whose 8x4 block the Gaussian can touch
   const int tg = blockIdx.x, b = tg / T, tile = tg % T;
   const uint32_t start = ranges[2 * tg], end = ranges[2 * tg + 1];
   const int n = (int)(end - start);
@@ -130,13 +131,29 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   const int my_slot = slot_of_lane(lane);
+  const float tile_x0 = (float)((tile % gx) * kTile), tile_y0 = (float)((tile / gx) * kTile);
+  auto build_mask = [&](int cc) {   // one thread per record of chunk cc (see warp_cull_mask)
+    const int sl = cc % kBwdStages;
+    const int h2 = Mx - cc * kBwdChunk, l2 = max(0, h2 - kBwdChunk), cn = h2 - l2;
+    if ((int)threadIdx.x < cn) {
+      mbar_wait(&s_bar[sl], (uint32_t)((cc / kBwdStages) & 1));
+      const float4 A = s_rec[sl][3 * threadIdx.x], Bq = s_rec[sl][3 * threadIdx.x + 1];
+      s_mask[cc % 3][threadIdx.x] = (uint8_t)warp_cull_mask(A.x, A.y, A.z, A.w, Bq.x, Bq.y, tile_x0, tile_y0);
+    }
+  };
+  if (nchunks > 0) build_mask(0);
+  __syncthreads();
 
   for (int c = 0; c < nchunks; c++) {
     const int slot = c % kBwdStages, pb = c & 1;
     const int hi = Mx - c * kBwdChunk, lo = max(0, hi - kBwdChunk), cnt = hi - lo;
     mbar_wait(&s_bar[slot], (uint32_t)((c / kBwdStages) & 1));
     const float4* r = s_rec[slot];
-    for (int j = cnt - 1; j >= 0; j--) {
+    const uint8_t* mk = s_mask[c % 3];
+    uint32_t bits = __ballot_sync(0xffffffffu, lane < cnt && ((mk[lane] >> warp) & 1));
+    while (bits) {          // back to front over the records that can touch this warp's pixels
+      const int j = 31 - __clz(bits);
+      bits &= ~(1u << j);
       const int pos = lo + j;
       const float4 A = r[3 * j], Bq = r[3 * j + 1];
       const float dx = __fsub_rn(Bq.x, pfx), dy = __fsub_rn(Bq.y, pfy);
@@ -188,6 +205,7 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
       const float red = reduce_scatter10(v, lane);
       if (my_slot >= 0) s_part[pb][j][warp][my_slot] = red;
     }
+    if (c + 1 < nchunks) build_mask(c + 1);
     __syncthreads();  // partials of this chunk complete; record slot free for reuse
     if (threadIdx.x == 0 && c + kBwdStages < nchunks) issue(c + kBwdStages);
     // cross-warp combine, one coalesced 48-byte row per instance (fixed order => deterministic)
@@ -195,8 +213,10 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
       const int rj = k / kGradF, vv = k % kGradF;
       float s = 0.0f;
       if (vv < kNVal) {
+        const uint32_t m = mk[rj];   // culled (warp, record) pairs wrote nothing
 #pragma unroll
-        for (int w = 0; w < kTilePix / 32; w++) s += s_part[pb][rj][w][vv];
+        for (int w = 0; w < kTilePix / 32; w++)
+          if ((m >> w) & 1) s += s_part[pb][rj][w][vv];
       }
       dst[(size_t)(lo + rj) * kGradF + vv] = s;
     }

@@ -151,6 +151,33 @@ __device__ __forceinline__ float pair_power(float dx, float dy, float cx, float 
                    -__fmul_rn(dy, __fmul_rn(dx, cy)));
 }
 
+// Conservative per-warp culling of a sorted record inside a tile: bit w of the result is 0 only
+// if NO pixel of warp w's 8x4 block (tile_pixel) can reach alpha >= 1/255 for this Gaussian, so
+// skipping the record for that warp changes nothing (the reference evaluates and rejects it per
+// pixel, forward.cu:344-349 / backward.cu:503-508). With the conic Q = [[a,b],[b,c]]:
+// power = -0.5 d^T Q d <= -0.5 lmin |d|^2, hence alpha <= o exp(-0.5 lmin dmin^2) where dmin is
+// the distance from the centre to the block; cull iff lmin dmin^2 > 2 ln(255 o) with a 0.1 % +
+// 0.01 safety margin (float error of the kernel's own power/exp evaluation is ~1e-6).
+// lmin = det / (mid + sqrt(mid^2 - det)) is the cancellation-free form of the small eigenvalue.
+__device__ __forceinline__ uint32_t warp_cull_mask(float a, float b, float c, float opacity, float cx, float cy,
+                                                   float tile_x0, float tile_y0) {
+  const float mid = 0.5f * (a + c), det = a * c - b * b;
+  const float disc = sqrtf(fmaxf(mid * mid - det, 0.0f));
+  const float lmin = det / (mid + disc);
+  if (!(det > 0.0f) || !(lmin > 0.0f) || !(opacity > 0.0f)) return 0xFFu;   // degenerate: never cull
+  const float thr = 2.0f * logf(255.0f * opacity) + 0.01f;
+  uint32_t m = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const float bx0 = tile_x0 + (float)((w & 1) << 3), by0 = tile_y0 + (float)((w >> 1) << 2);
+    const float ddx = fmaxf(fmaxf(bx0 - cx, cx - (bx0 + 7.0f)), 0.0f);
+    const float ddy = fmaxf(fmaxf(by0 - cy, cy - (by0 + 3.0f)), 0.0f);
+    const float d2 = ddx * ddx + ddy * ddy;
+    if (!(lmin * d2 * 0.999f > thr)) m |= 1u << w;
+  }
+  return m;
+}
+
 // pixel handled by thread t of a tile CTA: warps cover 8x4 pixel blocks (compact footprint).
 __device__ __forceinline__ void tile_pixel(int t, int& lx, int& ly) {
   const int w = t >> 5, l = t & 31;

@@ -512,6 +512,7 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
              float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib) {
   __shared__ __align__(128) float4 s_rec[kFwdStages][kFwdChunk * 3];
   __shared__ __align__(8) uint64_t s_bar[kFwdStages];
+  __shared__ uint8_t s_mask[kFwdStages][kFwdChunk];   // per record: which of the 8 warps can be touched
   const int tg = blockIdx.x, b = tg / T, tile = tg % T;
   const uint32_t start = ranges[2 * tg], end = ranges[2 * tg + 1];
   const int n = (int)(end - start);
@@ -539,6 +540,19 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   uint32_t last_contributor = 0;
   int issued = min(kFwdStages, nchunks);  // tracked identically by every thread
   int c = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float tile_x0 = (float)((tile % gx) * kTile), tile_y0 = (float)((tile / gx) * kTile);
+  // cull masks of chunk `cc` (one thread per record), written before the barrier that precedes its use
+  auto build_mask = [&](int cc) {
+    const int sl = cc % kFwdStages, cn = min(kFwdChunk, n - cc * kFwdChunk);
+    if ((int)threadIdx.x < cn) {
+      mbar_wait(&s_bar[sl], (uint32_t)((cc / kFwdStages) & 1));
+      const float4 A = s_rec[sl][3 * threadIdx.x], Bq = s_rec[sl][3 * threadIdx.x + 1];
+      s_mask[sl][threadIdx.x] = (uint8_t)warp_cull_mask(A.x, A.y, A.z, A.w, Bq.x, Bq.y, tile_x0, tile_y0);
+    }
+  };
+  if (nchunks > 0) build_mask(0);
+  __syncthreads();
   for (; c < nchunks; c++) {
     const int slot = c % kFwdStages;
     mbar_wait(&s_bar[slot], (uint32_t)((c / kFwdStages) & 1));
@@ -546,9 +560,16 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
     {
       // Branch-free body + __syncwarp keeps the 32 pixels of a warp converged: with `continue`
       // in the loop the lanes drift apart and the warp issues each lane group separately.
+      // Records whose footprint cannot reach this warp's 8x4 block are skipped warp-uniformly.
       const float4* r = s_rec[slot];
-      for (int j = 0; j < cnt; j++) {
-        if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // whole warp finished
+      for (int h = 0; h < cnt; h += 32) {
+        const bool mine = h + lane < cnt && ((s_mask[slot][h + lane] >> warp) & 1);
+        uint32_t bits = __ballot_sync(0xffffffffu, mine);
+        bool finished = false;
+        while (bits) {
+        const int j = h + __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (__ballot_sync(0xffffffffu, !done) == 0u) { finished = true; break; }  // whole warp finished
         const float4 A = r[3 * j], Bq = r[3 * j + 1];
         const float dx = __fsub_rn(Bq.x, pfx), dy = __fsub_rn(Bq.y, pfy);
         const float power = pair_power(dx, dy, A.x, A.y, A.z);
@@ -567,8 +588,11 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
           last_contributor = (uint32_t)(c * kFwdChunk + j + 1);
         }
         __syncwarp();
+        }
+        if (finished) break;
       }
     }
+    if (c + 1 < nchunks) build_mask(c + 1);
     const int ndone = __syncthreads_count(done);  // also orders slot reuse after all reads
     if (ndone == kTilePix) { c++; break; }
     if (c + kFwdStages < nchunks) {
