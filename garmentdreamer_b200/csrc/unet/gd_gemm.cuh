@@ -47,6 +47,8 @@ struct GemmKParams {
   int stages;
   int m_tiles, n_tiles, total_tiles;
   int stg_bufs;               // staging buffers per epilogue warp (1 or 2; 0 = no staging area)
+  int bias_stride;            // floats of bias staging per epilogue warp: 32 x ceil(chunks / 2)
+  int b_resident;             // CTA pairs with one N tile: the CTA's half of B (all k-blocks) is loaded once and stays in smem
   int tma_store;              // MODE 0: full 32-column chunks leave through shared memory + TMA store (tmC)
   int ksplit, kb_per_split;   // split-K: tile t covers k-blocks [ks*kb_per_split, ...) and writes fp32 partials
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
@@ -181,13 +183,18 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_bytes = kBM * kBK * 2, b_bytes = (uint32_t)(TWO ? BN / 2 : BN) * kBK * 2;   // per CTA
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
   const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-  uint8_t* stg_all = smem + (size_t)S * stage_bytes;   // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
+  const bool bres = TWO && p.b_resident;
+  if (bres && smem != smem_raw) __trap();   // resident mode is sized without the alignment slack (the base is 1 KB aligned)
+  const uint32_t b_slot = (b_bytes + 1023) & ~1023u;
+  const uint32_t stage_bytes = bres ? a_bytes : a_bytes + b_slot;       // resident B: the ring holds A only
+  uint8_t* b_res = smem + (size_t)S * stage_bytes;                      // [num_kb][b_slot] when resident
+  uint8_t* stg_all = b_res + (bres ? (size_t)p.num_kb * b_slot : 0);    // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + (size_t)kEpiWarps * p.stg_bufs * 2048);
   uint64_t* empty = full + S;
   uint64_t* tmem_full = empty + S;      // [2]
   uint64_t* tmem_empty = tmem_full + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bres_full = tmem_empty + 2; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 2);   // +2: keeps the bias area behind it 16-byte aligned
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,6 +206,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < S; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
     for (int s = 0; s < 2; s++) { bar_init(&tmem_full[s], 1); bar_init(&tmem_empty[s], TWO ? 2 * kEpiWarps : kEpiWarps); }
+    bar_init(bres_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -221,6 +229,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       // ---------------- TMA producer ----------------
       int it = 0;  // ring position, runs across tiles
+      if (bres) {   // this CTA's half of the (single) B tile, every k-block, once: it is reused by all M tiles
+        if (rank == 0) bar_expect_tx(bres_full, 2u * (uint32_t)p.num_kb * b_bytes);
+        for (int kb = 0; kb < p.num_kb; kb++)
+          tma_load_3d_2sm(b_res + (size_t)kb * b_slot, &tmB, bres_full, kb * kBK, (int)rank * (BN / 2), 0);
+      }
       for (int t = tile0; t < total; t += tile_step) {
         const int ks = t % p.ksplit, tt = t / p.ksplit;
         const int n_blk = tt % n_tiles, z = tt / (n_tiles * m_tiles);
@@ -249,14 +262,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + a_bytes;
           if (TWO) {
             // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of the pair
-            if (rank == 0) bar_expect_tx(&full[s], 2 * (a_bytes + b_bytes));
+            if (rank == 0) bar_expect_tx(&full[s], bres ? 2 * a_bytes : 2 * (a_bytes + b_bytes));
             if (p.mode_conv) {
               const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
               tma_load_4d_2sm(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
             } else {
               tma_load_4d_2sm(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
             }
-            tma_load_3d_2sm(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, b_c2);
+            if (!bres) tma_load_3d_2sm(sb, &tmB, &full[s], zh * p.b_head_k + kb * kBK, b_c1, b_c2);
           } else {
             bar_expect_tx(&full[s], a_bytes + b_bytes);
             if (p.mode_conv) {
@@ -274,6 +287,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------- MMA issuer (TWO: the leader CTA only) ----------------
     const uint32_t idesc = TWO ? (umma_idesc_f16(BN) + ((uint32_t)(kBM >> 4) << 24)) : umma_idesc_f16(BN);   // TWO: M = 256
     int it = 0, lt = 0;
+    if (bres) bar_wait(bres_full, 0);
     for (int t = tile0; t < total; t += tile_step, lt++) {
       const int acc = lt & 1;
       bar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator
@@ -287,7 +301,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
-          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(bres ? s2u(b_res + (size_t)kb * b_slot) : sa + a_bytes);
           if (TWO) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; k++)
@@ -313,7 +327,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3, half = (warp - 2) >> 2;
     constexpr bool geglu = MODE == 1, transposed = MODE == 2, splitk = MODE == 3;
     const int chunks = (BN + 31) / 32;
-    float* sb = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * 128;   // [4 chunks][32] bias sums
+    float* sb = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * p.bias_stride;   // [chunks of this warp][32] bias sums
     // output staging for the TMA store: 2 x [32 rows x 64 B] per warp, 64B-swizzled, 1024-aligned
     uint8_t* stg_base = stg_all + (size_t)(warp - 2) * p.stg_bufs * 2048;
     uint32_t st_cnt = 0;
@@ -335,6 +349,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
 #pragma unroll
       for (int ci = 0; ci < 4; ci++) {
+        if (ci * 32 >= p.bias_stride) break;
         const int n = n_blk * BN + (half + 2 * ci) * 32 + lane;
         float bsum = 0.f;
         if (half + 2 * ci < chunks && n < nlim && !splitk) {

@@ -633,16 +633,34 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
   // one persistent CTA per SM owns the shared memory: operand ring + epilogue staging + barriers/bias
-  const size_t smem_max = 227 * 1024, fixed = 1024 + 256 + 64 + gdu::kEpiWarps * 128 * sizeof(float);
+  const int bias_stride = 32 * ((((BN + 31) / 32) + 1) / 2);   // bias floats per epilogue warp
+  p.bias_stride = bias_stride;
+  const size_t smem_max = 227 * 1024, fixed_noslack = 256 + 64 + (size_t)gdu::kEpiWarps * bias_stride * sizeof(float);
+  const size_t fixed = 1024 + fixed_noslack;
   const bool mode0 = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED));
   const bool tma_ok = mode0 && (a->ldc % 8) == 0 && (a->c_batch_stride % 8) == 0 && (a->c_head_stride % 8) == 0 &&
                       ((uintptr_t)a->C % 16) == 0 && (a->heads == 1 || a->c_head_stride > 0) &&
                       (a->batch == a->heads || a->c_batch_stride > 0);
-  int stg_bufs = tma_ok ? 2 : 0;
+  static const bool use_tma_store = []() { const char* e = getenv("GD_GEMM_TMA_STORE"); return e && e[0] == '1'; }();
+  int stg_bufs = tma_ok ? (use_tma_store ? 2 : 1) : 0;   // the synchronous staged store needs one buffer per warp
   int stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
   if (tma_ok && stages < 4) {
     stg_bufs = 1;
     stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
+  }
+  // CTA pairs whose B tile is the same for every output tile (one N tile, no batch): keep this CTA's half of B
+  // resident in shared memory for the whole kernel; the ring then streams A only
+  // (measured neutral on B200 -- 128->128 conv at 512^2: 367 us resident vs 378 us streamed -- so it is opt-in: GD_GEMM_BRES=1)
+  static const bool bres_enabled = []() { const char* e = getenv("GD_GEMM_BRES"); return e && e[0] == '1'; }();
+  p.b_resident = 0;
+  if (bres_enabled && two && n_tiles_all == 1 && a->batch == 1 && a->heads == 1) {
+    const size_t a_bytes = (size_t)gdu::kBM * gdu::kBK * 2;
+    const size_t b_slot = (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
+    const size_t res = (size_t)num_kb_all * b_slot, stg = (size_t)gdu::kEpiWarps * stg_bufs * 2048;
+    if (res + stg + fixed_noslack + 3 * a_bytes <= smem_max && (size_t)m_tiles_all * a->batch >= 4 * 148) {
+      p.b_resident = 1;
+      stages = (int)((smem_max - fixed_noslack - stg - res) / a_bytes);
+    }
   }
   if (stages > 6) stages = 6;   // deeper rings measured no faster (profiles/r01_gemm_pair_stage_sweep.txt)
   if (stages < 2) stages = 2;
@@ -663,7 +681,10 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     p.ws = ws;
   }
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
-  const size_t smem = stages * stage_bytes + (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed;
+  const size_t smem = p.b_resident
+                          ? (size_t)stages * gdu::kBM * gdu::kBK * 2 + (size_t)num_kb_all * (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023) +
+                                (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed_noslack
+                          : stages * stage_bytes + (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed;
   // output tensor map for the staged epilogue: [batch][head][M][N], 32 x 32 box, 64B swizzle
   CUtensorMap tmC = tmA;
   p.tma_store = 0;
@@ -676,7 +697,6 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     const int rc = make_map(&tmC, a->C, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != GD_UNET_OK) return rc;
     // 2 = staged + coalesced st.global (default); 1 = staged + TMA store (GD_GEMM_TMA_STORE=1)
-    static const bool use_tma_store = []() { const char* e = getenv("GD_GEMM_TMA_STORE"); return e && e[0] == '1'; }();
     p.tma_store = use_tma_store ? 1 : 2;
   }
   static int num_sms = 0;
