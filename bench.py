@@ -326,6 +326,8 @@ def main():
     if sds_roofline is not None:
         sds_roofline["raster_bwd"] = roofline
         roofline = sds_roofline
+        from garmentdreamer_b200 import sds_step as _probe
+        roofline["dominant_kernels"] = _probe.dominant_gemm_probe(dev, peaks)
         if guidance.vae is not None:
             from garmentdreamer_b200 import sds_step as _s
             roofline["vae"] = {"bound": "tensor", "kernel": "VAE encode + input-gradient backward (k_gemm_tcgen05 conv-GEMM + GroupNorm sweeps)",

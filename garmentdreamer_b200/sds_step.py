@@ -119,5 +119,43 @@ class SdsBenchStep:
         return r
 
 
+def dominant_gemm_probe(dev, peaks):
+    """Live CUDA-event timing of the two GEMM shapes that carry the largest share of the step
+    (ncu launch list in profiles/): the 128->128 3x3 convolution of the VAE at 4x512^2 (8 launches
+    per step) and the 1280->1280 3x3 convolution of the UNet at 8x16^2 (7 launches). 20 launches of
+    each are captured in a CUDA graph; burst peak = a kernel timed alone."""
+    out = []
+    peak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained"))
+    for name, (N_, H, W, Ci, Co), traffic in (("k_gemm_tcgen05<0,1> conv 128->128 @4x512^2 (VAE)", (4, 512, 512, 128, 128), 507.5e6),
+                                              ("k_gemm_tcgen05<0,1> conv 1280->1280 @8x16^2 (UNet)", (8, 16, 16, 1280, 1280), None)):
+        x = torch.randn(N_, H, W, Ci, device=dev).half()
+        w = (torch.randn(Co, 9 * Ci, device=dev) * (9 * Ci) ** -0.5).half()
+        b = torch.randn(Co, device=dev).half()
+        y = torch.empty(N_, H, W, Co, device=dev, dtype=torch.float16)
+        ops.conv3x3(x, w, b, out=y)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                ops.conv3x3(x, w, b, out=y)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 60 * 1e3
+        flops = 2.0 * N_ * H * W * 9 * Ci * Co
+        ach = flops / us / 1e6
+        out.append({"kernel": name, "bound": "tensor", "launch_us": us, "algorithmic_flops": flops, "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": traffic,   # dram read+write bytes per launch from the committed ncu --set full capture, or None
+                    "traffic_source": "profiles/r01_s7_gemm_conv128_512sq_details.txt" if traffic else None})
+        del g
+    return out
+
+
 def make_bench_guidance(dev, views, use_vae=True):
     return SdsBenchStep(dev, views, use_vae=use_vae)
