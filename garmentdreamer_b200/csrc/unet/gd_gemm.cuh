@@ -401,7 +401,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int n0 = n_blk * BN + c0;
         if (n0 >= nlim) continue;                 // warp-uniform
-        if (p.flags & 0x200u) continue;           // timing experiment only (tools/gemm_probe.py): epilogue math + stores skipped
+        if (p.flags & GD_EPI_PROBE_SKIP) continue;   // timing experiment only: epilogue math + stores skipped
         const bool full32 = n0 + 32 <= nlim;
         if (!(MODE == 0 && p.tma_store && full32) && !row_ok) continue;   // the staged paths need the whole warp
         if constexpr (splitk) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel

@@ -32,6 +32,8 @@ typedef struct CUstream_st* gd_ustream_t; /* == cudaStream_t */
 #define GD_EPI_SILU 1u        /* y = silu(y) after bias */
 #define GD_EPI_TRANSPOSED 2u  /* store y^T (per batch): element (m,n) at C[n*ldc + m] */
 #define GD_EPI_GEGLU 4u       /* weight rows interleaved (value, gate) in blocks of 16: out[m, n/2] */
+#define GD_EPI_PROBE_SKIP 0x200u /* timing experiments only (tools/gemm_probe2.py): the epilogue drains TMEM but
+                                    computes and stores nothing -- output undefined; never set by the product */
 
 typedef struct {
   /* problem: C[z][M,N] (+)= A[z][M,K] * B[z][N,K]^T, fp16 in, fp32 accumulate, fp16 out */
