@@ -44,6 +44,11 @@ def make_case(name):
         P, W, H = 300, 48, 48
         g = garment(P, 5); cam = _look_at_camera(3.0, H, W)
         g["xyz"] = g["xyz"] + torch.tensor([100.0, 0.0, 0.0])
+    elif name == "dense_tile":  # > 2 x 4096 instances in each of the 4 central tiles (chunked-merge sort path)
+        P, W, H = 9000, 64, 64
+        g = garment(P, 6); cam = _look_at_camera(2.5, H, W)
+        g["xyz"] = torch.from_numpy(rng.normal(0, 0.012, (P, 3)).astype(np.float32))
+        g["opacity"] = torch.from_numpy(rng.uniform(0.01, 0.08, (P, 1)).astype(np.float32))
     elif name == "c1":  # BASELINE config 1 geometry: 10k Gaussians, 1 camera 256^2
         P, W, H = 10000, 256, 256
         g = garment(P, 0); cam = sample_cameras(4, H, W)[1]
