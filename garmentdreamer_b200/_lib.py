@@ -24,6 +24,8 @@ class GdCounters(ctypes.Structure):
         ("num_rendered", ctypes.c_uint32),
         ("overflow", ctypes.c_uint32),
         ("view_base", ctypes.c_uint32 * (GD_MAX_VIEWS + 1)),
+        ("bwd_items", ctypes.c_uint32),
+        ("bwd_next", ctypes.c_uint32),
     ]
 
 

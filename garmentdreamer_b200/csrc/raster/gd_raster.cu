@@ -132,7 +132,7 @@ int gd_raster_forward(const GdFwdArgs* a, gd_stream_t stream_) {
     GD_LAUNCH_CHECK("k_preprocess");
   }
   gd::k_spine<<<2, 1024, 0, stream>>>(B * nblkP, s.scan_partials, B * T, T, B, s.tile_count,
-                                      s.tile_cursor, s.ranges, s.counters, a->max_rendered);
+                                      s.tile_cursor, s.ranges, s.seg_base, s.counters, a->max_rendered);
   GD_LAUNCH_CHECK("k_spine");
   if (P > 0) {
     gd::k_scatter<<<dim3(nblkP, B), gd::kBlk, 0, stream>>>(P, gx, T, s.tiles_touched,
@@ -145,7 +145,8 @@ int gd_raster_forward(const GdFwdArgs* a, gd_stream_t stream_) {
   }
   gd::k_render_fwd<<<B * T, gd::kTilePix, 0, stream>>>(W, H, gx, T, s.ranges, s.sorted_rec,
                                                        a->background, a->out_color, a->out_depth,
-                                                       a->out_alpha, s.n_contrib);
+                                                       a->out_alpha, s.n_contrib, s.fin, s.fin_T, s.seg_base,
+                                                       s.ckpt, s.items, s.counters);
   GD_LAUNCH_CHECK("k_render_fwd");
   if (a->debug) {
     const cudaError_t e = cudaStreamSynchronize(stream);
@@ -175,9 +176,19 @@ int gd_raster_backward(const GdBwdArgs* a, gd_stream_t stream_) {
   gd::ViewPack vp;
   rc = make_views(a->views, B, W, H, vp);
   if (rc != GD_OK) return rc;
-  gd::k_render_bwd<<<B * T, gd::kTilePix, 0, stream>>>(
-      W, H, gx, T, s.ranges, s.sorted_rec, a->background, a->out_alpha, s.n_contrib, a->dL_dcolor,
-      a->dL_ddepth, a->dL_dalpha, s.inst_grad);
+  // persistent CTAs pull (tile, segment) items from the queue the forward compositor filled
+  static int bwd_grid = 0;
+  if (!bwd_grid) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gd::k_render_bwd, gd::kTilePix, 0);
+    bwd_grid = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  cudaMemsetAsync(&s.counters->bwd_next, 0, sizeof(uint32_t), stream);
+  gd::k_render_bwd<<<bwd_grid, gd::kTilePix, 0, stream>>>(
+      W, H, gx, T, s.ranges, s.seg_base, s.items, s.counters, s.sorted_rec, a->background, a->out_alpha,
+      s.n_contrib, s.fin, s.fin_T, s.ckpt, a->dL_dcolor, a->dL_ddepth, a->dL_dalpha, s.inst_grad);
   GD_LAUNCH_CHECK("k_render_bwd");
   gd::BwdOut out{a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity, a->dL_dmeans3D, a->dL_dcov3D,
                  a->shs ? a->dL_dsh : nullptr, a->scales ? a->dL_dscales : nullptr,
@@ -186,7 +197,7 @@ int gd_raster_backward(const GdBwdArgs* a, gd_stream_t stream_) {
   gd::k_bwd_epilogue<<<(P + gd::kBlk - 1) / gd::kBlk, gd::kBlk, 0, stream>>>(
       P, a->D, a->M, B, W, H, a->means3D, a->shs, a->scales, a->scale_modifier, a->rotations,
       cov3D, vp, a->radii, s.tiles_touched, s.point_offsets, s.clamped, s.inst_slot, s.inst_grad,
-      a->sum_views, out);
+      s.counters, a->sum_views, out);
   GD_LAUNCH_CHECK("k_bwd_epilogue");
   if (a->debug) {
     const cudaError_t e = cudaStreamSynchronize(stream);

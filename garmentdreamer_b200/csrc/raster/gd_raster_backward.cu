@@ -64,163 +64,183 @@ __device__ __forceinline__ float reduce_scatter10(const float (&v)[kNVal], int l
   return d;
 }
 
-// Kernel B1: one CTA per (view, tile), one thread per pixel; walks the tile's sorted records
-// back to front (only the part some pixel of the tile actually blended), staged by bulk TMA.
-__global__ void __launch_bounds__(kTilePix)
+// Kernel B1: persistent CTAs (one thread per pixel of a tile) pull work items (tile, list segment)
+// from the queue the forward compositor filled. An item replays records [s*kSeg, min(Mx,(s+1)*kSeg))
+// of the tile's sorted list back to front, staged by bulk TMA. The per-pixel compositor state at
+// the upper end of the segment comes from the forward checkpoint at that boundary:
+//   T (transmittance before the boundary record) and, per channel, the normalised colour behind it
+//   A = (C_final - C_prefix) / T   (alpha channel: 1 - T_final / T),
+// which is exactly what the reference's back-to-front recurrence (backward.cu:518-556) holds when
+// it reaches that record; the top segment starts from (T_final, 0) like the reference. Segments of
+// one tile are independent work items, so a 3000-record tile no longer serialises one CTA.
+__global__ void __launch_bounds__(kTilePix, 4)
 k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
-             const float* __restrict__ sorted_rec, const float* __restrict__ bg,
-             const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
-             const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpix_depth,
-             const float* __restrict__ dL_dalphas, float* __restrict__ inst_grad) {
+             const uint32_t* __restrict__ seg_base, const uint2* __restrict__ items,
+             GdCounters* __restrict__ counters, const float* __restrict__ sorted_rec,
+             const float* __restrict__ bg, const float* __restrict__ alphas,
+             const uint32_t* __restrict__ n_contrib, const float4* __restrict__ fin,
+             const float* __restrict__ fin_T, const float* __restrict__ ckpt, const float* __restrict__ dL_dpixels,
+             const float* __restrict__ dL_dpix_depth, const float* __restrict__ dL_dalphas,
+             float* __restrict__ inst_grad) {
   __shared__ __align__(128) float4 s_rec[kBwdStages][kBwdChunk * 3];
-  __shared__ __align__(16) float s_part[2][kBwdChunk][kTilePix / 32][kGradF];
+  __shared__ __align__(16) float s_part[2][kTilePix / 32][kBwdChunk][kGradF];   // [buffer][warp][record][value]
+  __shared__ uint32_t s_wrote[2][kTilePix / 32];   // per warp: records of the chunk it wrote partials for
   __shared__ __align__(8) uint64_t s_bar[kBwdStages];
   __shared__ int s_max[kTilePix / 32];
-  __shared__ uint8_t s_mask[3][kBwdChunk];   // per record: warps whose 8x4 block the Gaussian can touch
-  const int tg = blockIdx.x, b = tg / T, tile = tg % T;
-  const uint32_t start = ranges[2 * tg], end = ranges[2 * tg + 1];
-  const int n = (int)(end - start);
-  if (n == 0) return;
+  __shared__ uint32_t s_item;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int lx, ly;
   tile_pixel(threadIdx.x, lx, ly);
-  const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
-  const bool inside = px < W && py < H;
-  const float pfx = (float)px, pfy = (float)py;
-  const size_t N = (size_t)W * H, pix = (size_t)py * W + px;
-  const int my_last = inside ? (int)n_contrib[(size_t)b * N + pix] : 0;
-  {
-    const int wm = __reduce_max_sync(0xffffffffu, my_last);
-    if (lane == 0) s_max[warp] = wm;
-  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBwdStages; s++) mbar_init(&s_bar[s], 1);
     mbar_fence_init();
   }
-  __syncthreads();
-  int Mx = 0;
-#pragma unroll
-  for (int w = 0; w < kTilePix / 32; w++) Mx = max(Mx, s_max[w]);
-  // chunk c covers list positions [lo_c, hi_c), hi_c = Mx - c*chunk
-  const int nchunks = (Mx + kBwdChunk - 1) / kBwdChunk;
-  const float* src = sorted_rec + (size_t)start * kRecF;
-  float* dst = inst_grad + (size_t)start * kGradF;
-  auto issue = [&](int c) {
-    const int hi = Mx - c * kBwdChunk, lo = max(0, hi - kBwdChunk);
-    const uint32_t bytes = (uint32_t)(hi - lo) * kRecF * 4;
-    const int slot = c % kBwdStages;
-    mbar_expect_tx(&s_bar[slot], bytes);
-    tma_load_1d(s_rec[slot], src + (size_t)lo * kRecF, bytes, &s_bar[slot]);
-  };
-  if (threadIdx.x == 0)
-    for (int c = 0; c < kBwdStages && c < nchunks; c++) issue(c);
-  // instances no pixel reached get zero rows
-  for (int k = Mx * kGradF + threadIdx.x; k < n * kGradF; k += kTilePix) dst[k] = 0.0f;
-
-  float Tfin = 0.f, dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f, dLa = 0.f;
-  if (inside) {
-    Tfin = 1.0f - alphas[(size_t)b * N + pix];
-    const float* dp = dL_dpixels + (size_t)b * 3 * N;
-    dLp0 = dp[pix]; dLp1 = dp[N + pix]; dLp2 = dp[2 * N + pix];
-    dLd = dL_dpix_depth[(size_t)b * N + pix];
-    dLa = dL_dalphas[(size_t)b * N + pix];
-  }
-  float Tr = Tfin;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
-  float acc_d = 0.f, acc_a = 0.f, last_alpha = 0.f, last_depth = 0.f;
-  const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  const size_t N = (size_t)W * H;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   const int my_slot = slot_of_lane(lane);
-  const float tile_x0 = (float)((tile % gx) * kTile), tile_y0 = (float)((tile / gx) * kTile);
-  auto build_mask = [&](int cc) {   // one thread per record of chunk cc (see warp_cull_mask)
-    const int sl = cc % kBwdStages;
-    const int h2 = Mx - cc * kBwdChunk, l2 = max(0, h2 - kBwdChunk), cn = h2 - l2;
-    if ((int)threadIdx.x < cn) {
-      mbar_wait(&s_bar[sl], (uint32_t)((cc / kBwdStages) & 1));
-      const float4 A = s_rec[sl][3 * threadIdx.x], Bq = s_rec[sl][3 * threadIdx.x + 1];
-      s_mask[cc % 3][threadIdx.x] = (uint8_t)warp_cull_mask(A.x, A.y, A.z, A.w, Bq.x, Bq.y, tile_x0, tile_y0);
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  const uint32_t n_items = counters->bwd_items;
+  uint32_t g = 0;   // chunks this CTA has pushed through the ring so far (slot = g % stages, parity from g / stages)
+  for (;;) {
+    __syncthreads();   // previous item completely finished (s_item, s_max, s_part, ring)
+    if (threadIdx.x == 0) s_item = atomicAdd(&counters->bwd_next, 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const uint2 it = items[item];
+    const int tg = (int)it.x, seg = (int)it.y, b = tg / T, tile = tg % T;
+    const uint32_t start = ranges[2 * tg], end = ranges[2 * tg + 1];
+    const int n = (int)(end - start);
+    const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
+    const bool inside = px < W && py < H;
+    const float pfx = (float)px, pfy = (float)py;
+    const size_t pix = (size_t)py * W + px;
+    const int my_last = inside ? (int)n_contrib[(size_t)b * N + pix] : 0;
+    {
+      const int wm = __reduce_max_sync(0xffffffffu, my_last);
+      if (lane == 0) s_max[warp] = wm;
     }
-  };
-  if (nchunks > 0) build_mask(0);
-  __syncthreads();
+    __syncthreads();
+    int Mx = 0;
+#pragma unroll
+    for (int w = 0; w < kTilePix / 32; w++) Mx = max(Mx, s_max[w]);
+    const int seg_lo = seg * kSeg, seg_hi = min(Mx, seg_lo + kSeg);
+    const bool top = seg_lo + kSeg >= Mx;
+    // chunk c covers list positions [max(seg_lo, hi_c - chunk), hi_c), hi_c = seg_hi - c*chunk
+    const int nchunks = seg_hi > seg_lo ? (seg_hi - seg_lo + kBwdChunk - 1) / kBwdChunk : 0;
+    const float* src = sorted_rec + (size_t)start * kRecF;
+    float* dst = inst_grad + (size_t)start * kGradF;
+    auto issue = [&](int c) {
+      const int hi = seg_hi - c * kBwdChunk, lo = max(seg_lo, hi - kBwdChunk);
+      const uint32_t bytes = (uint32_t)(hi - lo) * kRecF * 4;
+      const int slot = (int)((g + (uint32_t)c) % kBwdStages);
+      mbar_expect_tx(&s_bar[slot], bytes);
+      tma_load_1d(s_rec[slot], src + (size_t)lo * kRecF, bytes, &s_bar[slot]);
+    };
+    if (threadIdx.x == 0)
+      for (int c = 0; c < kBwdStages && c < nchunks; c++) issue(c);
+    if (seg == 0) {   // instances no pixel reached get zero rows (written by the tile's first segment)
+      float4* z = reinterpret_cast<float4*>(dst);
+      for (int k = Mx * 3 + (int)threadIdx.x; k < n * 3; k += kTilePix) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float Tfin = 0.f, dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f, dLa = 0.f;
+    float Tr = 0.f, A0 = 0.f, A1 = 0.f, A2 = 0.f, Ad = 0.f, Aa = 0.f;
+    if (inside && my_last > seg_lo) {
+      Tfin = 1.0f - alphas[(size_t)b * N + pix];
+      const float* dp = dL_dpixels + (size_t)b * 3 * N;
+      dLp0 = dp[pix]; dLp1 = dp[N + pix]; dLp2 = dp[2 * N + pix];
+      dLd = dL_dpix_depth[(size_t)b * N + pix];
+      dLa = dL_dalphas[(size_t)b * N + pix];
+      Tr = Tfin;
+      if (!top) {
+        const float* ck = ckpt + (size_t)(seg_base[tg] + (uint32_t)seg) * (kCkptF * kTilePix) + threadIdx.x;
+        const float4 f = fin[(size_t)b * N + pix];
+        const float Tb = ck[0], iT = 1.0f / Tb;
+        // the reference reaches this record with T = (1 - alpha_out) / prod_{j >= boundary}(1 - alpha_j): it
+        // starts from the ROUNDED 1 - sum(alpha T) (backward.cu:463), whose relative error at opaque pixels
+        // (T_final ~ 1e-4) is ~1e-4 -- keep that factor so the gradients agree with it to float rounding
+        const float ratio = fin_T[(size_t)b * N + pix] * iT;   // prod_{j >= boundary}(1 - alpha_j)
+        Tr = Tfin / ratio;
+        A0 = (f.x - ck[kTilePix]) * iT; A1 = (f.y - ck[2 * kTilePix]) * iT; A2 = (f.z - ck[3 * kTilePix]) * iT;
+        Ad = (f.w - ck[4 * kTilePix]) * iT;
+        Aa = 1.0f - ratio;
+      }
+    }
+    const float bg_dot = bg0 * dLp0 + bg1 * dLp1 + bg2 * dLp2;
 
-  for (int c = 0; c < nchunks; c++) {
-    const int slot = c % kBwdStages, pb = c & 1;
-    const int hi = Mx - c * kBwdChunk, lo = max(0, hi - kBwdChunk), cnt = hi - lo;
-    mbar_wait(&s_bar[slot], (uint32_t)((c / kBwdStages) & 1));
-    const float4* r = s_rec[slot];
-    const uint8_t* mk = s_mask[c % 3];
-    uint32_t bits = __ballot_sync(0xffffffffu, lane < cnt && ((mk[lane] >> warp) & 1));
-    while (bits) {          // back to front over the records that can touch this warp's pixels
-      const int j = 31 - __clz(bits);
-      bits &= ~(1u << j);
-      const int pos = lo + j;
-      const float4 A = r[3 * j], Bq = r[3 * j + 1];
-      const float dx = __fsub_rn(Bq.x, pfx), dy = __fsub_rn(Bq.y, pfy);
-      const float power = pair_power(dx, dy, A.x, A.y, A.z);
-      const float G = expf(power);
-      const float alpha = fminf(0.99f, __fmul_rn(A.w, G));
-      const bool contrib = (pos < my_last) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-      if (__ballot_sync(0xffffffffu, contrib) == 0u) {
-        if (lane < kGradF) s_part[pb][j][warp][lane] = 0.0f;
-        continue;
-      }
-      float v[kNVal];
+    for (int c = 0; c < nchunks; c++) {
+      const int slot = (int)((g + (uint32_t)c) % kBwdStages), pb = c & 1;
+      const int hi = seg_hi - c * kBwdChunk, lo = max(seg_lo, hi - kBwdChunk), cnt = hi - lo;
+      mbar_wait(&s_bar[slot], (uint32_t)(((g + (uint32_t)c) / kBwdStages) & 1u));
+      const float4* r = s_rec[slot];
+      uint32_t bits = __ballot_sync(0xffffffffu, lane < cnt && ((__float_as_uint(r[3 * lane + 2].w) >> warp) & 1u));
+      uint32_t wrote = 0;
+      while (bits) {          // back to front over the records that can touch this warp's pixels
+        const int j = 31 - __clz(bits);
+        bits &= ~(1u << j);
+        const int pos = lo + j;
+        const float4 A = r[3 * j], Bq = r[3 * j + 1];
+        const float dx = __fsub_rn(Bq.x, pfx), dy = __fsub_rn(Bq.y, pfy);
+        const float power = pair_power(dx, dy, A.x, A.y, A.z);
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, __fmul_rn(A.w, G));
+        const bool contrib = (pos < my_last) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+        if (__ballot_sync(0xffffffffu, contrib) == 0u) continue;
+        float v[kNVal];
 #pragma unroll
-      for (int k = 0; k < kNVal; k++) v[k] = 0.0f;
-      if (contrib) {
-        const float4 Cq = r[3 * j + 2];
-        Tr = Tr / (1.0f - alpha);
-        const float dchannel_dcolor = alpha * Tr;
-        float dL_dopa = 0.0f;
-        acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0; lc0 = Bq.w;
-        dL_dopa += (Bq.w - acc0) * dLp0;
-        acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1; lc1 = Cq.x;
-        dL_dopa += (Cq.x - acc1) * dLp1;
-        acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2; lc2 = Cq.y;
-        dL_dopa += (Cq.y - acc2) * dLp2;
-        v[6] = dchannel_dcolor * dLp0;
-        v[7] = dchannel_dcolor * dLp1;
-        v[8] = dchannel_dcolor * dLp2;
-        acc_d = last_alpha * last_depth + (1.0f - last_alpha) * acc_d;
-        last_depth = Bq.z;
-        dL_dopa += (Bq.z - acc_d) * dLd;
-        v[9] = dchannel_dcolor * dLd;
-        acc_a = last_alpha + (1.0f - last_alpha) * acc_a;
-        dL_dopa += (1.0f - acc_a) * dLa;
-        dL_dopa *= Tr;
-        last_alpha = alpha;
-        dL_dopa += (-Tfin / (1.0f - alpha)) * bg_dot;
-        const float dL_dG = A.w * dL_dopa;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * A.x - gdy * A.y;
-        const float dG_ddely = -gdy * A.z - gdx * A.y;
-        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-        v[1] = dL_dG * dG_ddely * ddely_dy;
-        v[2] = -0.5f * gdx * dx * dL_dG;
-        v[3] = -0.5f * gdx * dy * dL_dG;
-        v[4] = -0.5f * gdy * dy * dL_dG;
-        v[5] = G * dL_dopa;
+        for (int k = 0; k < kNVal; k++) v[k] = 0.0f;
+        if (contrib) {
+          const float4 Cq = r[3 * j + 2];
+          const float om = 1.0f - alpha;
+          const float inv = __fdividef(1.0f, om);
+          Tr = Tr * inv;
+          const float dchannel_dcolor = alpha * Tr;
+          float dL_dopa = (Bq.w - A0) * dLp0;
+          dL_dopa += (Cq.x - A1) * dLp1;
+          dL_dopa += (Cq.y - A2) * dLp2;
+          dL_dopa += (Bq.z - Ad) * dLd;
+          dL_dopa += (1.0f - Aa) * dLa;
+          dL_dopa *= Tr;
+          dL_dopa -= Tfin * inv * bg_dot;
+          // colour behind the NEXT (nearer) record: the reference's accum_rec recurrence
+          A0 = alpha * Bq.w + om * A0; A1 = alpha * Cq.x + om * A1; A2 = alpha * Cq.y + om * A2;
+          Ad = alpha * Bq.z + om * Ad; Aa = alpha + om * Aa;
+          v[6] = dchannel_dcolor * dLp0;
+          v[7] = dchannel_dcolor * dLp1;
+          v[8] = dchannel_dcolor * dLp2;
+          v[9] = dchannel_dcolor * dLd;
+          const float dL_dG = A.w * dL_dopa;
+          const float gdx = G * dx, gdy = G * dy;
+          const float dG_ddelx = -gdx * A.x - gdy * A.y;
+          const float dG_ddely = -gdy * A.z - gdx * A.y;
+          v[0] = dL_dG * dG_ddelx * ddelx_dx;
+          v[1] = dL_dG * dG_ddely * ddely_dy;
+          v[2] = -0.5f * gdx * dx * dL_dG;
+          v[3] = -0.5f * gdx * dy * dL_dG;
+          v[4] = -0.5f * gdy * dy * dL_dG;
+          v[5] = G * dL_dopa;
+        }
+        const float red = reduce_scatter10(v, lane);
+        if (my_slot >= 0) s_part[pb][warp][j][my_slot] = red;
+        wrote |= 1u << j;
       }
-      const float red = reduce_scatter10(v, lane);
-      if (my_slot >= 0) s_part[pb][j][warp][my_slot] = red;
-    }
-    if (c + 1 < nchunks) build_mask(c + 1);
-    __syncthreads();  // partials of this chunk complete; record slot free for reuse
-    if (threadIdx.x == 0 && c + kBwdStages < nchunks) issue(c + kBwdStages);
-    // cross-warp combine, one coalesced 48-byte row per instance (fixed order => deterministic)
-    for (int k = threadIdx.x; k < cnt * kGradF; k += kTilePix) {
-      const int rj = k / kGradF, vv = k % kGradF;
-      float s = 0.0f;
-      if (vv < kNVal) {
-        const uint32_t m = mk[rj];   // culled (warp, record) pairs wrote nothing
+      if (lane == 0) s_wrote[pb][warp] = wrote;
+      __syncthreads();  // partials of this chunk complete; record slot free for reuse
+      if (threadIdx.x == 0 && c + kBwdStages < nchunks) issue(c + kBwdStages);
+      // cross-warp combine, one coalesced 48-byte row per instance (fixed order => deterministic)
+      for (int k = threadIdx.x; k < cnt * kGradF; k += kTilePix) {
+        const int rj = k / kGradF, vv = k % kGradF;
+        float s = 0.0f;
+        if (vv < kNVal) {
 #pragma unroll
-        for (int w = 0; w < kTilePix / 32; w++)
-          if ((m >> w) & 1) s += s_part[pb][rj][w][vv];
+          for (int w = 0; w < kTilePix / 32; w++)
+            if ((s_wrote[pb][w] >> rj) & 1u) s += s_part[pb][w][rj][vv];
+        }
+        dst[(size_t)(lo + rj) * kGradF + vv] = s;
       }
-      dst[(size_t)(lo + rj) * kGradF + vv] = s;
+      // s_part[pb] / s_wrote[pb] are rewritten two chunks later, after the next chunk's __syncthreads
     }
-    // s_part[pb] is rewritten two chunks later, after the next chunk's __syncthreads
+    g += (uint32_t)nchunks;
   }
 }
 
@@ -327,7 +347,7 @@ k_bwd_epilogue(int P, int D, int M, int B, int W, int H, const float* __restrict
                const uint32_t* __restrict__ tiles_touched,
                const uint32_t* __restrict__ point_offsets, const uint8_t* __restrict__ clamped,
                const uint32_t* __restrict__ inst_slot, const float* __restrict__ inst_grad,
-               int sum_views, BwdOut out) {
+               const GdCounters* __restrict__ counters, int sum_views, BwdOut out) {
   __shared__ float s_view[GD_MAX_VIEWS][36];
   for (int k = threadIdx.x; k < B * 35; k += blockDim.x) {
     const int b = k / 35, e = k % 35;
@@ -337,6 +357,9 @@ k_bwd_epilogue(int P, int D, int M, int B, int W, int H, const float* __restrict
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < P;
   const int lane = threadIdx.x & 31;
+  // instance-arena overflow in the forward: nothing was rendered (blank ranges, no instance rows),
+  // so every gradient is an exact zero -- never touch inst_slot / inst_grad (uninitialised)
+  const bool arena_ok = counters->overflow == 0u;
   float mx = 0, my = 0, mz = 0, c3[6] = {0, 0, 0, 0, 0, 0};
   if (live) {
     mx = means3D[3 * (size_t)i]; my = means3D[3 * (size_t)i + 1]; mz = means3D[3 * (size_t)i + 2];
@@ -345,7 +368,7 @@ k_bwd_epilogue(int P, int D, int M, int B, int W, int H, const float* __restrict
   }
   for (int b = 0; b < B; b++) {
     const size_t g = (size_t)b * P + i;
-    const bool vis = live && radii[g] > 0;
+    const bool vis = live && arena_ok && radii[g] > 0;
     const uint32_t n = vis ? tiles_touched[g] : 0u;
     const uint32_t off = vis ? point_offsets[g] - n : 0u;
     // ---- gather-reduce the instance rows ----

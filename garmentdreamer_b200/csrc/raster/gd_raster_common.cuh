@@ -12,6 +12,8 @@ constexpr int kRecF = 12;                // floats per per-(view,Gaussian) recor
 constexpr int kGradF = 12;               // floats per per-instance gradient row (48 B)
 constexpr int kBlk = 256;                // Gaussians per block in the per-Gaussian kernels
 constexpr int kSortCap = 4096;           // keys sorted in shared memory per pass
+constexpr int kSeg = 512;                // sorted records per backward work item (list segment of one tile)
+constexpr int kCkptF = 5;                // floats per pixel in a forward checkpoint: T, C0, C1, C2, D
 
 // Per-view constants, passed by value as a kernel parameter (<= 32 * 40 B).
 struct ViewDev {
@@ -39,12 +41,17 @@ struct State {
   uint32_t* ranges;       // [B*T,2]
   uint32_t* tile_count;   // [B*T]
   uint32_t* tile_cursor;  // [B*T]
+  float4* fin;            // [B*N] forward accumulators (C0, C1, C2, D) before the background term
+  float* fin_T;           // [B*N] final transmittance as the forward's running product
+  uint32_t* seg_base;     // [B*T] exclusive scan of the interior segment boundaries of each tile
   // binning
   uint64_t* tile_keys;   // [cap]
   uint32_t* point_list;  // [cap]
   float* sorted_rec;     // [cap,12]
   uint32_t* inst_slot;   // [cap]
   float* inst_grad;      // [cap,12]
+  float* ckpt;           // [cap/kSeg + 1][kCkptF][256] per-pixel compositor state at segment boundaries
+  uint2* items;          // [cap/kSeg + B*T + 1] backward work queue: (global tile, segment)
   size_t geom_bytes, binning_bytes, img_bytes;
 };
 
@@ -79,6 +86,9 @@ inline State carve_state(int P, int W, int H, int B, uint32_t cap, void* geom, v
   carve(p, s.ranges, (size_t)B * T * 2);
   carve(p, s.tile_count, (size_t)B * T);
   carve(p, s.tile_cursor, (size_t)B * T);
+  carve(p, s.fin, (size_t)B * N);
+  carve(p, s.fin_T, (size_t)B * N);
+  carve(p, s.seg_base, (size_t)B * T);
   s.img_bytes = (size_t)(p - p0) + 128;
   p = reinterpret_cast<char*>(binning);
   p0 = p;
@@ -87,6 +97,8 @@ inline State carve_state(int P, int W, int H, int B, uint32_t cap, void* geom, v
   carve(p, s.sorted_rec, (size_t)cap * kRecF);
   carve(p, s.inst_slot, (size_t)cap);
   carve(p, s.inst_grad, (size_t)cap * kGradF);
+  carve(p, s.ckpt, ((size_t)cap / kSeg + 1) * kCkptF * kTilePix);
+  carve(p, s.items, (size_t)cap / kSeg + (size_t)B * T + 1);
   s.binning_bytes = (size_t)(p - p0) + 128;
   return s;
 }
@@ -154,26 +166,39 @@ __device__ __forceinline__ float pair_power(float dx, float dy, float cx, float 
 // Conservative per-warp culling of a sorted record inside a tile: bit w of the result is 0 only
 // if NO pixel of warp w's 8x4 block (tile_pixel) can reach alpha >= 1/255 for this Gaussian, so
 // skipping the record for that warp changes nothing (the reference evaluates and rejects it per
-// pixel, forward.cu:344-349 / backward.cu:503-508). With the conic Q = [[a,b],[b,c]]:
-// power = -0.5 d^T Q d <= -0.5 lmin |d|^2, hence alpha <= o exp(-0.5 lmin dmin^2) where dmin is
-// the distance from the centre to the block; cull iff lmin dmin^2 > 2 ln(255 o) with a 0.1 % +
-// 0.01 safety margin (float error of the kernel's own power/exp evaluation is ~1e-6).
-// lmin = det / (mid + sqrt(mid^2 - det)) is the cancellation-free form of the small eigenvalue.
+// pixel, forward.cu:344-349 / backward.cu:503-508). With the conic Q = [[a,b],[b,c]] and
+// d = centre - pixel: alpha = o exp(-0.5 q(d)), q(d) = a dx^2 + 2 b dx dy + c dy^2, so the block is
+// culled iff min over the block's rectangle of q exceeds 2 ln(255 o) (0.1 % + 0.01 margin; the float
+// error of the kernels' own power/exp evaluation is ~1e-6). q is convex: its minimum over a
+// rectangle that does not contain the centre lies on one of the four edges, where it is a clamped
+// 1-D parabola. Computed ONCE per instance by k_tile_sort and stored in the sorted record.
 __device__ __forceinline__ uint32_t warp_cull_mask(float a, float b, float c, float opacity, float cx, float cy,
                                                    float tile_x0, float tile_y0) {
-  const float mid = 0.5f * (a + c), det = a * c - b * b;
-  const float disc = sqrtf(fmaxf(mid * mid - det, 0.0f));
-  const float lmin = det / (mid + disc);
-  if (!(det > 0.0f) || !(lmin > 0.0f) || !(opacity > 0.0f)) return 0xFFu;   // degenerate: never cull
+  const float det = a * c - b * b;
+  if (!(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f) || !(opacity > 0.0f) || !(cx == cx) || !(cy == cy))
+    return 0xFFu;   // degenerate or NaN: never cull
   const float thr = 2.0f * logf(255.0f * opacity) + 0.01f;
+  const float ia = 1.0f / a, ic = 1.0f / c;
   uint32_t m = 0;
 #pragma unroll
   for (int w = 0; w < 8; w++) {
     const float bx0 = tile_x0 + (float)((w & 1) << 3), by0 = tile_y0 + (float)((w >> 1) << 2);
-    const float ddx = fmaxf(fmaxf(bx0 - cx, cx - (bx0 + 7.0f)), 0.0f);
-    const float ddy = fmaxf(fmaxf(by0 - cy, cy - (by0 + 3.0f)), 0.0f);
-    const float d2 = ddx * ddx + ddy * ddy;
-    if (!(lmin * d2 * 0.999f > thr)) m |= 1u << w;
+    // d ranges over [xl, xh] x [yl, yh]
+    const float xl = cx - (bx0 + 7.0f), xh = cx - bx0, yl = cy - (by0 + 3.0f), yh = cy - by0;
+    float qmin = 0.0f;
+    if (!(xl <= 0.0f && xh >= 0.0f && yl <= 0.0f && yh >= 0.0f)) {
+      qmin = 3.0e38f;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float X = e ? xh : xl;
+        const float y = fminf(yh, fmaxf(yl, -b * X * ic));
+        qmin = fminf(qmin, a * X * X + 2.0f * b * X * y + c * y * y);
+        const float Y = e ? yh : yl;
+        const float x = fminf(xh, fmaxf(xl, -b * Y * ia));
+        qmin = fminf(qmin, a * x * x + 2.0f * b * x * Y + c * Y * Y);
+      }
+    }
+    if (!(qmin * 0.999f > thr)) m |= 1u << w;
   }
   return m;
 }

@@ -293,7 +293,8 @@ __device__ uint32_t block_exclusive_scan_inplace(uint32_t* data, int n) {
 __global__ void __launch_bounds__(1024)
 k_spine(int nblk, uint32_t* __restrict__ scan_partials, int BT, int T, int B,
         const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
-        uint32_t* __restrict__ ranges, GdCounters* __restrict__ counters, uint32_t cap) {
+        uint32_t* __restrict__ ranges, uint32_t* __restrict__ seg_base,
+        GdCounters* __restrict__ counters, uint32_t cap) {
   if (blockIdx.x == 0) {
     const uint32_t total = block_exclusive_scan_inplace(scan_partials, nblk);
     if (threadIdx.x == 0) scan_partials[nblk] = total;
@@ -315,7 +316,16 @@ k_spine(int nblk, uint32_t* __restrict__ scan_partials, int BT, int T, int B,
     counters->num_rendered = total;
     counters->overflow = overflow ? 1u : 0u;
     counters->view_base[B] = total;
+    counters->bwd_items = 0u;   // the forward compositor queues the backward work items
+    counters->bwd_next = 0u;
   }
+  // checkpoint slots: a tile with c instances has (c-1)/kSeg interior segment boundaries
+  for (int k = threadIdx.x; k < BT; k += blockDim.x) {
+    const uint32_t c = tile_count[k];
+    seg_base[k] = (c == 0 || overflow) ? 0u : (c - 1) / (uint32_t)kSeg;
+  }
+  __syncthreads();
+  block_exclusive_scan_inplace(seg_base, BT);
 }
 
 // Kernel 3: finishes the scan (point_offsets), stores each visible Gaussian's exclusive instance
@@ -490,7 +500,9 @@ k_tile_sort(int P, int gx, int T, const uint32_t* __restrict__ ranges,
     const float4* src = reinterpret_cast<const float4*>(rec + g * kRecF);
     const float4 r0 = src[0], r1 = src[1], r2 = src[2];
     float4* dst = reinterpret_cast<float4*>(sorted_rec + (size_t)(start + k) * kRecF);
-    dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    // sorted record: conic.xyz, opacity | px, py, depth, r | g, b, 0, per-warp cull mask (8 bits)
+    const uint32_t cull = warp_cull_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, (float)(tx * kTile), (float)(ty * kTile));
+    dst[0] = r0; dst[1] = r1; dst[2] = make_float4(r2.x, r2.y, 0.0f, __uint_as_float(cull));
     point_list[start + k] = idx;
     const uint32_t pk = __float_as_uint(r2.w);
     const int x0 = pk & 1023, y0 = (pk >> 10) & 1023, rw = pk >> 20;
@@ -501,18 +513,28 @@ k_tile_sort(int P, int gx, int T, const uint32_t* __restrict__ ranges,
 
 // Kernel 5: alpha compositor. One CTA per (view, tile), one thread per pixel. The tile's sorted
 // records are contiguous in memory and are streamed into a 4-slot shared-memory ring with bulk
-// TMA copies (cp.async.bulk + mbarrier); every thread walks the ring front to back.
+// TMA copies (cp.async.bulk + mbarrier); every thread walks the ring front to back. Each record
+// carries the 8-bit mask of the warps (8x4 pixel blocks) it can reach (k_tile_sort), so a warp only
+// visits its own records.
+// For the backward pass the kernel also leaves (a) the per-pixel accumulators before the background
+// term (`fin`), (b) a checkpoint (T, C, D per pixel) every kSeg records and (c) one work item per
+// list segment [s*kSeg, (s+1)*kSeg) that some pixel of the tile blended: k_render_bwd replays the
+// segments of a tile independently, which turns 1 long tile into several short work items.
 constexpr int kFwdChunk = 64;   // records per TMA copy (3 KB)
 constexpr int kFwdStages = 4;
+static_assert(kSeg % kFwdChunk == 0, "checkpoints are taken at chunk boundaries");
 
 __global__ void __launch_bounds__(kTilePix)
 k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
              const float* __restrict__ sorted_rec, const float* __restrict__ bg,
              float* __restrict__ out_color, float* __restrict__ out_depth,
-             float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib) {
+             float* __restrict__ out_alpha, uint32_t* __restrict__ n_contrib,
+             float4* __restrict__ fin, float* __restrict__ fin_T, const uint32_t* __restrict__ seg_base,
+             float* __restrict__ ckpt,
+             uint2* __restrict__ items, GdCounters* __restrict__ counters) {
   __shared__ __align__(128) float4 s_rec[kFwdStages][kFwdChunk * 3];
   __shared__ __align__(8) uint64_t s_bar[kFwdStages];
-  __shared__ uint8_t s_mask[kFwdStages][kFwdChunk];   // per record: which of the 8 warps can be touched
+  __shared__ uint32_t s_max[kTilePix / 32];
   const int tg = blockIdx.x, b = tg / T, tile = tg % T;
   const uint32_t start = ranges[2 * tg], end = ranges[2 * tg + 1];
   const int n = (int)(end - start);
@@ -541,20 +563,13 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   int issued = min(kFwdStages, nchunks);  // tracked identically by every thread
   int c = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float tile_x0 = (float)((tile % gx) * kTile), tile_y0 = (float)((tile / gx) * kTile);
-  // cull masks of chunk `cc` (one thread per record), written before the barrier that precedes its use
-  auto build_mask = [&](int cc) {
-    const int sl = cc % kFwdStages, cn = min(kFwdChunk, n - cc * kFwdChunk);
-    if ((int)threadIdx.x < cn) {
-      mbar_wait(&s_bar[sl], (uint32_t)((cc / kFwdStages) & 1));
-      const float4 A = s_rec[sl][3 * threadIdx.x], Bq = s_rec[sl][3 * threadIdx.x + 1];
-      s_mask[sl][threadIdx.x] = (uint8_t)warp_cull_mask(A.x, A.y, A.z, A.w, Bq.x, Bq.y, tile_x0, tile_y0);
-    }
-  };
-  if (nchunks > 0) build_mask(0);
-  __syncthreads();
+  float* ck = ckpt + (size_t)(n > 0 ? seg_base[tg] : 0u) * (kCkptF * kTilePix) + threadIdx.x;
   for (; c < nchunks; c++) {
     const int slot = c % kFwdStages;
+    if (c > 0 && (c * kFwdChunk) % kSeg == 0) {   // state after the first c*kFwdChunk records
+      float* o = ck + (size_t)((c * kFwdChunk) / kSeg - 1) * (kCkptF * kTilePix);
+      o[0] = Tr; o[kTilePix] = C0; o[2 * kTilePix] = C1; o[3 * kTilePix] = C2; o[4 * kTilePix] = Dp;
+    }
     mbar_wait(&s_bar[slot], (uint32_t)((c / kFwdStages) & 1));
     const int cnt = min(kFwdChunk, n - c * kFwdChunk);
     {
@@ -563,7 +578,7 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
       // Records whose footprint cannot reach this warp's 8x4 block are skipped warp-uniformly.
       const float4* r = s_rec[slot];
       for (int h = 0; h < cnt; h += 32) {
-        const bool mine = h + lane < cnt && ((s_mask[slot][h + lane] >> warp) & 1);
+        const bool mine = h + lane < cnt && ((__float_as_uint(r[3 * (h + lane) + 2].w) >> warp) & 1u);
         uint32_t bits = __ballot_sync(0xffffffffu, mine);
         bool finished = false;
         while (bits) {
@@ -592,7 +607,6 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
         if (finished) break;
       }
     }
-    if (c + 1 < nchunks) build_mask(c + 1);
     const int ndone = __syncthreads_count(done);  // also orders slot reuse after all reads
     if (ndone == kTilePix) { c++; break; }
     if (c + kFwdStages < nchunks) {
@@ -611,12 +625,27 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   if (inside) {
     const size_t N = (size_t)W * H, pix = (size_t)py * W + px;
     n_contrib[(size_t)b * N + pix] = last_contributor;
+    fin[(size_t)b * N + pix] = make_float4(C0, C1, C2, Dp);
+    fin_T[(size_t)b * N + pix] = Tr;
     float* oc = out_color + (size_t)b * 3 * N;
     oc[pix] = __fmaf_rn(Tr, bg[0], C0);
     oc[N + pix] = __fmaf_rn(Tr, bg[1], C1);
     oc[2 * N + pix] = __fmaf_rn(Tr, bg[2], C2);
     out_alpha[(size_t)b * N + pix] = weight;
     out_depth[(size_t)b * N + pix] = Dp;
+  }
+  if (n > 0) {   // queue the tile's backward work items: one per kSeg records that were blended (at least one)
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0) s_max[warp] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t mx = 0;
+#pragma unroll
+      for (int w = 0; w < kTilePix / 32; w++) mx = max(mx, s_max[w]);
+      const uint32_t nseg = mx == 0 ? 1u : (mx + kSeg - 1) / kSeg;
+      const uint32_t base = atomicAdd(&counters->bwd_items, nseg);
+      for (uint32_t sgi = 0; sgi < nseg; sgi++) items[base + sgi] = make_uint2((uint32_t)tg, nseg - 1 - sgi);
+    }
   }
 }
 

@@ -66,6 +66,8 @@ typedef struct {
   uint32_t num_rendered; /* total (Gaussian, tile) instances over all B views */
   uint32_t overflow;     /* 1 if num_rendered > max_rendered: outputs are blank, re-run bigger */
   uint32_t view_base[GD_MAX_VIEWS + 1]; /* first instance of each view in the global list */
+  uint32_t bwd_items;    /* backward work items (tile, list segment) queued by the forward compositor */
+  uint32_t bwd_next;     /* next item to hand out; reset by every gd_raster_backward call */
 } GdCounters;
 
 typedef struct {
