@@ -107,7 +107,7 @@ def raster_lib():
     global _raster
     if _raster is not None:
         return _raster
-    path = os.path.join(LIB_DIR, "libgd_raster.so")
+    path = os.environ.get("GD_RASTER_LIB") or os.path.join(LIB_DIR, "libgd_raster.so")   # override: tuning builds
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `make -C garmentdreamer_b200/csrc raster` "

@@ -194,7 +194,7 @@ int gd_raster_backward(const GdBwdArgs* a, gd_stream_t stream_) {
                  a->shs ? a->dL_dsh : nullptr, a->scales ? a->dL_dscales : nullptr,
                  a->scales ? a->dL_drotations : nullptr, a->dL_dconic, a->dL_ddepths};
   const float* cov3D = a->cov3D_precomp ? a->cov3D_precomp : s.cov3D;
-  gd::k_bwd_epilogue<<<(P + gd::kBlk - 1) / gd::kBlk, gd::kBlk, 0, stream>>>(
+  gd::k_bwd_epilogue<<<(P + gd::kEpiBlk - 1) / gd::kEpiBlk, gd::kEpiBlk, 0, stream>>>(
       P, a->D, a->M, B, W, H, a->means3D, a->shs, a->scales, a->scale_modifier, a->rotations,
       cov3D, vp, a->radii, s.tiles_touched, s.point_offsets, s.clamped, s.inst_slot, s.inst_grad,
       s.counters, a->sum_views, out);

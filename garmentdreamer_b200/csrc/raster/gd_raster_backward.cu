@@ -18,7 +18,13 @@ __device__ const float BSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
                                     -0.5900435899266435f};
 
 constexpr int kBwdChunk = 32;  // records per TMA copy and per cross-warp combine
-constexpr int kBwdStages = 4;
+#ifndef GD_BWD_STAGES
+#define GD_BWD_STAGES 3
+#endif
+#ifndef GD_BWD_CTAS
+#define GD_BWD_CTAS 4
+#endif
+constexpr int kBwdStages = GD_BWD_STAGES;
 constexpr int kNVal = 10;      // reduced values per (pixel, Gaussian) pair
 
 // Warp reduce-scatter of 10 values in 12 shuffles (5+3+2+1+1) instead of 50: after it, lane
@@ -69,30 +75,39 @@ __device__ __forceinline__ float reduce_scatter10(const float (&v)[kNVal], int l
 // of the tile's sorted list back to front, staged by bulk TMA. The per-pixel compositor state at
 // the upper end of the segment comes from the forward checkpoint at that boundary:
 //   T (transmittance before the boundary record) and, per channel, the normalised colour behind it
-//   A = (C_final - C_prefix) / T   (alpha channel: 1 - T_final / T),
+//   A = (C_final - C_prefix) / T   (alpha channel: 1 - prod_{j >= boundary}(1 - alpha_j)),
 // which is exactly what the reference's back-to-front recurrence (backward.cu:518-556) holds when
 // it reaches that record; the top segment starts from (T_final, 0) like the reference. Segments of
 // one tile are independent work items, so a 3000-record tile no longer serialises one CTA.
-__global__ void __launch_bounds__(kTilePix, 4)
+//
+// Inside an item the 8 warps are DECOUPLED: there is no block barrier per chunk. A warp waits for
+// the chunk's records (mbarrier of the TMA copy), walks the records whose cull mask names its 8x4
+// block, leaves its 10 reduced values per record in its own slice of the stage, and arrives on the
+// stage's counter. The warp that arrives last sums the slices in warp order (deterministic), writes
+// one coalesced 48-byte row per instance and refills the stage with the chunk kBwdStages ahead.
+// Warps whose block sees few records run ahead instead of idling at a barrier.
+__global__ void __launch_bounds__(kTilePix, GD_BWD_CTAS)
 k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
              const uint32_t* __restrict__ seg_base, const uint2* __restrict__ items,
              GdCounters* __restrict__ counters, const float* __restrict__ sorted_rec,
              const float* __restrict__ bg, const float* __restrict__ alphas,
              const uint32_t* __restrict__ n_contrib, const float4* __restrict__ fin,
-             const float* __restrict__ fin_T, const float* __restrict__ ckpt, const float* __restrict__ dL_dpixels,
-             const float* __restrict__ dL_dpix_depth, const float* __restrict__ dL_dalphas,
-             float* __restrict__ inst_grad) {
+             const float* __restrict__ fin_T, const float* __restrict__ ckpt,
+             const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpix_depth,
+             const float* __restrict__ dL_dalphas, float* __restrict__ inst_grad) {
+  constexpr int NW = kTilePix / 32;
   __shared__ __align__(128) float4 s_rec[kBwdStages][kBwdChunk * 3];
-  __shared__ __align__(16) float s_part[2][kTilePix / 32][kBwdChunk][kGradF];   // [buffer][warp][record][value]
-  __shared__ uint32_t s_wrote[2][kTilePix / 32];   // per warp: records of the chunk it wrote partials for
+  __shared__ __align__(16) float s_part[kBwdStages][NW][kBwdChunk][kGradF];   // [stage][warp][record][value]
+  __shared__ uint32_t s_wrote[kBwdStages][NW];   // per warp: records of the chunk it wrote partials for
+  __shared__ uint32_t s_cnt[kBwdStages];         // warps that finished the chunk in this stage
   __shared__ __align__(8) uint64_t s_bar[kBwdStages];
-  __shared__ int s_max[kTilePix / 32];
+  __shared__ int s_max[NW];
   __shared__ uint32_t s_item;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int lx, ly;
   tile_pixel(threadIdx.x, lx, ly);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBwdStages; s++) mbar_init(&s_bar[s], 1);
+    for (int s = 0; s < kBwdStages; s++) { mbar_init(&s_bar[s], 1); s_cnt[s] = 0u; }
     mbar_fence_init();
   }
   const size_t N = (size_t)W * H;
@@ -100,9 +115,9 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   const int my_slot = slot_of_lane(lane);
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
   const uint32_t n_items = counters->bwd_items;
-  uint32_t g = 0;   // chunks this CTA has pushed through the ring so far (slot = g % stages, parity from g / stages)
+  uint32_t g = 0;   // chunks this CTA has pushed through the ring so far (stage = g % stages, parity from g / stages)
   for (;;) {
-    __syncthreads();   // previous item completely finished (s_item, s_max, s_part, ring)
+    __syncthreads();   // previous item completely finished (s_item, s_max, ring, last combine)
     if (threadIdx.x == 0) s_item = atomicAdd(&counters->bwd_next, 1u);
     __syncthreads();
     const uint32_t item = s_item;
@@ -123,7 +138,7 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
     __syncthreads();
     int Mx = 0;
 #pragma unroll
-    for (int w = 0; w < kTilePix / 32; w++) Mx = max(Mx, s_max[w]);
+    for (int w = 0; w < NW; w++) Mx = max(Mx, s_max[w]);
     const int seg_lo = seg * kSeg, seg_hi = min(Mx, seg_lo + kSeg);
     const bool top = seg_lo + kSeg >= Mx;
     // chunk c covers list positions [max(seg_lo, hi_c - chunk), hi_c), hi_c = seg_hi - c*chunk
@@ -133,9 +148,9 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
     auto issue = [&](int c) {
       const int hi = seg_hi - c * kBwdChunk, lo = max(seg_lo, hi - kBwdChunk);
       const uint32_t bytes = (uint32_t)(hi - lo) * kRecF * 4;
-      const int slot = (int)((g + (uint32_t)c) % kBwdStages);
-      mbar_expect_tx(&s_bar[slot], bytes);
-      tma_load_1d(s_rec[slot], src + (size_t)lo * kRecF, bytes, &s_bar[slot]);
+      const int stage = (int)((g + (uint32_t)c) % kBwdStages);
+      mbar_expect_tx(&s_bar[stage], bytes);
+      tma_load_1d(s_rec[stage], src + (size_t)lo * kRecF, bytes, &s_bar[stage]);
     };
     if (threadIdx.x == 0)
       for (int c = 0; c < kBwdStages && c < nchunks; c++) issue(c);
@@ -169,10 +184,10 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
     const float bg_dot = bg0 * dLp0 + bg1 * dLp1 + bg2 * dLp2;
 
     for (int c = 0; c < nchunks; c++) {
-      const int slot = (int)((g + (uint32_t)c) % kBwdStages), pb = c & 1;
+      const int stage = (int)((g + (uint32_t)c) % kBwdStages);
       const int hi = seg_hi - c * kBwdChunk, lo = max(seg_lo, hi - kBwdChunk), cnt = hi - lo;
-      mbar_wait(&s_bar[slot], (uint32_t)(((g + (uint32_t)c) / kBwdStages) & 1u));
-      const float4* r = s_rec[slot];
+      mbar_wait(&s_bar[stage], (uint32_t)(((g + (uint32_t)c) / kBwdStages) & 1u));
+      const float4* r = s_rec[stage];
       uint32_t bits = __ballot_sync(0xffffffffu, lane < cnt && ((__float_as_uint(r[3 * lane + 2].w) >> warp) & 1u));
       uint32_t wrote = 0;
       while (bits) {          // back to front over the records that can touch this warp's pixels
@@ -221,24 +236,44 @@ k_render_bwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
           v[5] = G * dL_dopa;
         }
         const float red = reduce_scatter10(v, lane);
-        if (my_slot >= 0) s_part[pb][warp][j][my_slot] = red;
+        if (my_slot >= 0) s_part[stage][warp][j][my_slot] = red;
         wrote |= 1u << j;
       }
-      if (lane == 0) s_wrote[pb][warp] = wrote;
-      __syncthreads();  // partials of this chunk complete; record slot free for reuse
-      if (threadIdx.x == 0 && c + kBwdStages < nchunks) issue(c + kBwdStages);
-      // cross-warp combine, one coalesced 48-byte row per instance (fixed order => deterministic)
-      for (int k = threadIdx.x; k < cnt * kGradF; k += kTilePix) {
-        const int rj = k / kGradF, vv = k % kGradF;
-        float s = 0.0f;
-        if (vv < kNVal) {
-#pragma unroll
-          for (int w = 0; w < kTilePix / 32; w++)
-            if ((s_wrote[pb][w] >> rj) & 1u) s += s_part[pb][w][rj][vv];
-        }
-        dst[(size_t)(lo + rj) * kGradF + vv] = s;
+      // ---- arrive; the last warp of the chunk combines and refills the stage ----
+      __syncwarp();
+      uint32_t prev = 0;
+      if (lane == 0) {
+        s_wrote[stage][warp] = wrote;
+        __threadfence_block();                       // this warp's partials before its arrival
+        prev = atomicAdd(&s_cnt[stage], 1u);
       }
-      // s_part[pb] / s_wrote[pb] are rewritten two chunks later, after the next chunk's __syncthreads
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == NW - 1) {
+        __threadfence_block();                       // the other warps' partials after their arrivals
+        if (lane < cnt) {   // lane = record: sum the slices in warp order, one 48-byte row
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+#pragma unroll
+          for (int w = 0; w < NW; w++) {
+            if ((s_wrote[stage][w] >> lane) & 1u) {
+              const float4* pr = reinterpret_cast<const float4*>(&s_part[stage][w][lane][0]);
+              const float4 q0 = pr[0], q1 = pr[1], q2 = pr[2];
+              a0.x += q0.x; a0.y += q0.y; a0.z += q0.z; a0.w += q0.w;
+              a1.x += q1.x; a1.y += q1.y; a1.z += q1.z; a1.w += q1.w;
+              a2.x += q2.x; a2.y += q2.y;
+            }
+          }
+          float4* row = reinterpret_cast<float4*>(dst + (size_t)(lo + lane) * kGradF);
+          row[0] = a0; row[1] = a1; row[2] = make_float4(a2.x, a2.y, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s_cnt[stage] = 0u;
+          if (c + kBwdStages < nchunks) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the stage before the async refill
+            issue(c + kBwdStages);
+          }
+        }
+      }
     }
     g += (uint32_t)nchunks;
   }
@@ -339,7 +374,8 @@ __device__ __forceinline__ void put(float* p, size_t idx, float v, bool acc) {
 
 // Kernel B2: one thread per Gaussian, loop over views. Gathers and sums the Gaussian's instance
 // rows (in emission order: deterministic), then runs the whole per-Gaussian backward chain.
-__global__ void __launch_bounds__(kBlk)
+constexpr int kEpiBlk = 128;   // 6 CTAs of 128 threads per SM (<= 85 registers): 100k Gaussians fit in ONE wave of 148 SMs
+__global__ void __launch_bounds__(kEpiBlk, 6)
 k_bwd_epilogue(int P, int D, int M, int B, int W, int H, const float* __restrict__ means3D,
                const float* __restrict__ shs, const float* __restrict__ scales, float mod,
                const float* __restrict__ rotations, const float* __restrict__ cov3Ds,

@@ -12,7 +12,10 @@ constexpr int kRecF = 12;                // floats per per-(view,Gaussian) recor
 constexpr int kGradF = 12;               // floats per per-instance gradient row (48 B)
 constexpr int kBlk = 256;                // Gaussians per block in the per-Gaussian kernels
 constexpr int kSortCap = 4096;           // keys sorted in shared memory per pass
-constexpr int kSeg = 512;                // sorted records per backward work item (list segment of one tile)
+#ifndef GD_SEG
+#define GD_SEG 512
+#endif
+constexpr int kSeg = GD_SEG;                // sorted records per backward work item (list segment of one tile)
 constexpr int kCkptF = 5;                // floats per pixel in a forward checkpoint: T, C0, C1, C2, D
 
 // Per-view constants, passed by value as a kernel parameter (<= 32 * 40 B).
@@ -123,7 +126,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"   // suspend-time hint: no hot spinning
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
