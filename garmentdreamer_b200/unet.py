@@ -65,6 +65,9 @@ class UNetB200:
         self._graph_launches = 0
         self.dtype = torch.float16
         self.training = False
+        # test hook: callable(kind, name, input NHWC fp16, output NHWC fp16), called after every block in
+        # eager mode (tests/test_blocks_gpu.py compares each block with the fp32 restatement on the SAME input)
+        self._trace = None
 
     # ---- module-like surface used by the reference guidance ---------------------------------
     def eval(self):
@@ -93,6 +96,7 @@ class UNetB200:
     def _resnet(self, p, x, emb):
         w = self.w
         N, H, W, Cin = x.shape
+        x_in = x
         off, c = self._temb_off[p]
         temb = emb[:, off:off + c]   # emb = all time_emb_proj outputs [B, sum(Cout)], row stride sum(Cout)
         h = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=1e-5, silu=True)
@@ -101,7 +105,10 @@ class UNetB200:
         if p + ".conv_shortcut.weight" in w:
             x = ops.linear(x.view(N * H * W, Cin), w[p + ".conv_shortcut.weight"], w[p + ".conv_shortcut.bias"])
             x = x.view(N, H, W, -1)
-        return ops.conv3x3(h, w[p + ".conv2.weight"], w[p + ".conv2.bias"], residual=x)
+        out = ops.conv3x3(h, w[p + ".conv2.weight"], w[p + ".conv2.bias"], residual=x)
+        if self._trace is not None:
+            self._trace("resnet", p, x_in, out)
+        return out
 
     def _attention(self, p, xn, ctx, heads, resid):
         """xn [B,T,C] normalised tokens, ctx [B,Tk,Ck] (== xn for self-attention)."""
@@ -134,12 +141,16 @@ class UNetB200:
         f = ops.linear(n3, w[b + ".ff.net.0.proj.weight"], w[b + ".ff.net.0.proj.bias"], flags=ops.EPI_GEGLU)
         h = ops.linear(f, w[b + ".ff.net.2.weight"], w[b + ".ff.net.2.bias"], residual=h)
         out = ops.linear(h, w[p + ".proj_out.weight"], w[p + ".proj_out.bias"], residual=x.view(N, H * W, C))
+        if self._trace is not None:
+            self._trace("transformer", p, x, out.view(N, H, W, C))
         return out.view(N, H, W, C)
 
     # ---- forward -------------------------------------------------------------------------------
     def _forward_impl(self, sample, t_f32, ctx):
         w = self.w
         x = ops.conv_in(sample, w["conv_in.weight"], w["conv_in.bias"])
+        if self._trace is not None:
+            self._trace("in", "conv_in", sample, x)
         temb = ops.timestep_embedding(t_f32, 320)
         emb = ops.small_linear(temb, w["time_embedding.linear_1.weight"], w["time_embedding.linear_1.bias"], silu_out=True)
         # every consumer (ResnetBlock2D.time_emb_proj) applies SiLU first: do it once here
@@ -156,7 +167,9 @@ class UNetB200:
                 skips.append(x)
             if i < 3:
                 p = f"down_blocks.{i}.downsamplers.0.conv"
-                x = ops.conv3x3_stride2(x, w[p + ".weight"], w[p + ".bias"])
+                x_in, x = x, ops.conv3x3_stride2(x, w[p + ".weight"], w[p + ".bias"])
+                if self._trace is not None:
+                    self._trace("down", p, x_in, x)
                 skips.append(x)
         x = self._resnet("mid_block.resnets.0", x, emb)
         x = self._transformer("mid_block.attentions.0", x, ctx, 20)
@@ -170,9 +183,15 @@ class UNetB200:
                     x = self._transformer(f"up_blocks.{i}.attentions.{j}", x, ctx, rev_heads[i])
             if i < 3:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
-                x = ops.conv3x3(ops.upsample2x(x), w[p + ".weight"], w[p + ".bias"])
+                x_in, x = x, ops.conv3x3(ops.upsample2x(x), w[p + ".weight"], w[p + ".bias"])
+                if self._trace is not None:
+                    self._trace("up", p, x_in, x)
+        x_in = x
         x = ops.groupnorm(x, w["conv_norm_out.weight"], w["conv_norm_out.bias"], eps=1e-5, silu=True)
-        return ops.conv_out(x, w["conv_out.weight"], w["conv_out.bias"])  # NCHW fp32 (fp16-rounded)
+        out = ops.conv_out(x, w["conv_out.weight"], w["conv_out.bias"])  # NCHW fp32 (fp16-rounded)
+        if self._trace is not None:
+            self._trace("out", "conv_out", x_in, out)
+        return out
 
     def forward_f32(self, sample, timestep, encoder_hidden_states):
         """sample [B,4,H,W] (any float dtype, NCHW), timestep [B], ctx [B,77,1024] -> fp32 NCHW."""

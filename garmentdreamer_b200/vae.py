@@ -81,6 +81,9 @@ class VAEEncoderB200:
             m = sd[f"{a}.{n}.weight"]
             self.w[f"{a}.{n}.fwd"], self.w[f"{a}.{n}.bwd"] = h(m), h(m.t())
         self._saved = None
+        # test hook: callable(kind, name, input, output) after every forward block, and
+        # callable(kind + "_bwd", name, (block input, upstream gradient), input gradient) after every backward block
+        self._trace = None
 
     # ---- module-like surface ---------------------------------------------------------------
     def eval(self):
@@ -104,6 +107,8 @@ class VAEEncoderB200:
             sc = ops.linear(x.view(N * H * W, C), w[p + ".conv_shortcut.fwd"], w[p + ".conv_shortcut.bias"]).view(N, H, W, -1)
         out = ops.conv3x3(n2, w[p + ".conv2.fwd"], w[p + ".conv2.bias"], residual=sc)
         saved.append(("resnet", p, x, st1, h1, st2))
+        if self._trace is not None:
+            self._trace("resnet", p, x, out)
         return out
 
     def _resnet_bwd(self, rec, dout):
@@ -116,14 +121,21 @@ class VAEEncoderB200:
         if p + ".conv_shortcut.bwd" in w:
             N, H, W, C = dout.shape
             add = ops.linear(dout.view(N * H * W, C), w[p + ".conv_shortcut.bwd"]).view(N, H, W, -1)
-        return ops.groupnorm_bwd(x, dn1, w[p + ".norm1.weight"], w[p + ".norm1.bias"], st1, silu=True, add=add, out=dn1)
+        keep = dout.clone() if self._trace is not None else None
+        din = ops.groupnorm_bwd(x, dn1, w[p + ".norm1.weight"], w[p + ".norm1.bias"], st1, silu=True, add=add, out=dn1)
+        if self._trace is not None:
+            self._trace("resnet_bwd", p, (x, keep), din)
+        return din
 
     def _down_fwd(self, p, x, saved):
         s2d = ops.space_to_depth(x)
         C = x.shape[-1]
         taps = [(dx, dy, ph * C) for dx, dy, ph in _DOWN_TAPS]
         saved.append(("down", p, C))
-        return ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"])
+        out = ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"])
+        if self._trace is not None:
+            self._trace("down", p, x, out)
+        return out
 
     def _down_bwd(self, rec, dout):
         _, p, C = rec
@@ -132,7 +144,10 @@ class VAEEncoderB200:
         for ph in range(4):
             taps = [(-(kx >> 1), -(ky >> 1), 0) for ky in range(3) for kx in range(3) if (ky & 1) * 2 + (kx & 1) == ph]
             ops.conv_taps(dout, self.w[f"{p}.bwd{ph}"], taps, Cout, out=ds2d[..., ph * C:(ph + 1) * C])
-        return ops.depth_to_space(ds2d)
+        din = ops.depth_to_space(ds2d)
+        if self._trace is not None:
+            self._trace("down_bwd", p, (None, dout), din)
+        return din
 
     def _attn_fwd(self, p, x, saved):
         w = self.w
@@ -148,6 +163,8 @@ class VAEEncoderB200:
         o = ops.bmm_nt(P, ops.transpose(v))                    # P @ v
         out = ops.linear(o, w[p + ".to_out.0.fwd"], w[p + ".to_out.0.bias"], residual=x.view(N, T, C)).view(N, H, W, C)
         saved.append(("attn", p, x, st, q, k, v, P, scale))
+        if self._trace is not None:
+            self._trace("attn", p, x, out)
         return out
 
     def _attn_bwd(self, rec, dout):
@@ -163,8 +180,11 @@ class VAEEncoderB200:
         dhn = ops.linear(dq, w[p + ".to_q.bwd"])
         dhn = ops.linear(dk, w[p + ".to_k.bwd"], residual=dhn, out=dhn)
         dhn = ops.linear(dv, w[p + ".to_v.bwd"], residual=dhn, out=dhn)
-        return ops.groupnorm_bwd(x, dhn.view(N, H, W, C), w[p + ".group_norm.weight"], w[p + ".group_norm.bias"], st,
-                                 silu=False, add=dout)
+        din = ops.groupnorm_bwd(x, dhn.view(N, H, W, C), w[p + ".group_norm.weight"], w[p + ".group_norm.bias"], st,
+                                silu=False, add=dout)
+        if self._trace is not None:
+            self._trace("attn_bwd", p, (x, dout), din)
+        return din
 
     # ---- forward / backward ------------------------------------------------------------------
     def encode(self, imgs, noise, keep_for_backward=True, input_range="01", scaling=SCALING):

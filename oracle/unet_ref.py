@@ -158,40 +158,54 @@ def transformer(sd, p, x, ctx, heads):
     return h + res
 
 
-def unet_forward(sd, sample, timestep, encoder_hidden_states):
-    """sample [B,4,H,W], timestep [B], encoder_hidden_states [B,77,1024]; dtype = that of sd."""
+def unet_forward(sd, sample, timestep, encoder_hidden_states, trace=None):
+    """sample [B,4,H,W], timestep [B], encoder_hidden_states [B,77,1024]; dtype = that of sd.
+    trace: optional callable(name, output NCHW) invoked after every block (error-growth tables)."""
+    tr = trace if trace is not None else (lambda name, out: None)
     dt = sd["conv_in.weight"].dtype
     x = sample.to(dt)
     ctx = encoder_hidden_states.to(dt)
     temb = timestep_embedding(timestep.to(dt)).to(dt)  # timesteps arrive in weights dtype (:155)
     emb = _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", temb)))
     x = F.conv2d(x, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
+    tr("conv_in", x)
     skips = [x]
     for i in range(4):
         for j in range(2):
             x = resnet(sd, f"down_blocks.{i}.resnets.{j}", x, emb)
+            tr(f"down_blocks.{i}.resnets.{j}", x)
             if CFG["down_attn"][i]:
                 x = transformer(sd, f"down_blocks.{i}.attentions.{j}", x, ctx, CFG["heads"][i])
+                tr(f"down_blocks.{i}.attentions.{j}", x)
             skips.append(x)
         if i < 3:
             p = f"down_blocks.{i}.downsamplers.0.conv"
             x = F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], stride=2, padding=1)
+            tr(p, x)
             skips.append(x)
     x = resnet(sd, "mid_block.resnets.0", x, emb)
+    tr("mid_block.resnets.0", x)
     x = transformer(sd, "mid_block.attentions.0", x, ctx, 20)
+    tr("mid_block.attentions.0", x)
     x = resnet(sd, "mid_block.resnets.1", x, emb)
+    tr("mid_block.resnets.1", x)
     rev_heads = list(reversed(CFG["heads"]))
     for i in range(4):
         for j in range(3):
             x = torch.cat([x, skips.pop()], 1)
             x = resnet(sd, f"up_blocks.{i}.resnets.{j}", x, emb)
+            tr(f"up_blocks.{i}.resnets.{j}", x)
             if CFG["up_attn"][i]:
                 x = transformer(sd, f"up_blocks.{i}.attentions.{j}", x, ctx, rev_heads[i])
+                tr(f"up_blocks.{i}.attentions.{j}", x)
         if i < 3:
             p = f"up_blocks.{i}.upsamplers.0.conv"
             x = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), sd[p + ".weight"], sd[p + ".bias"], padding=1)
+            tr(p, x)
     x = F.silu(_gn(sd, "conv_norm_out", x, 1e-5))
-    return F.conv2d(x, sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
+    x = F.conv2d(x, sd["conv_out.weight"], sd["conv_out.bias"], padding=1)
+    tr("conv_out", x)
+    return x
 
 
 def alphas_cumprod(n=1000, beta_start=0.00085, beta_end=0.012):

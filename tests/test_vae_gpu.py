@@ -1,15 +1,24 @@
 """GPU: the B200 VAE encoder forward + input-gradient backward against the PyTorch restatement
 (oracle/vae_ref.py, "parity unpinned": diffusers is not available offline) and its autograd.
 
-Tolerance: like the UNet (tests/test_unet_gpu.py) two fp16 evaluations of the network differ from
-the fp32 result by more than 1e-3, so each test measures the error of the PyTorch-eager fp16
-restatement (what the reference executes) against fp32 and requires ours to be no worse than
-max(1e-3, 1.5 x that)."""
+Asserted in absolute numbers (no ratio to another fp16 run):
+  * every block, forward and backward, is within 1e-3 of fp32 on the same input
+    (tests/test_blocks_gpu.py, measured <= 4.4e-4);
+  * whole encoder: latents within LAT_TOL = 1e-3 (north_star's tolerance; measured 5.7e-4);
+    d/d image within GRAD_TOL = 5e-3: the backward chains 14 forward + 14 backward blocks, each
+    adding an independent fp16 rounding of <= 4.4e-4 on top of the forward's, i.e.
+    sqrt(28 + 14) * 4.4e-4 ~ 3e-3 (measured 3.5e-3; PyTorch-eager fp16 autograd: 4.6e-3, printed);
+  * both also at the c2 shape (4 x 512^2);
+  * StableDiffusionGuidance.__call__ (a10) by VALUE against an fp32 restatement of
+    stable_diffusion_guidance.py:374-448."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+
+
+LAT_TOL, GRAD_TOL = 1e-3, 5e-3
 
 
 def rel(a, b):
@@ -97,7 +106,7 @@ def test_softmax_bwd_transpose_bmm():
 
 
 # ---- whole encoder ---------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,res", [(2, 128), (1, 256), (1, 512)])
+@pytest.mark.parametrize("B,res", [(2, 128), (1, 256), (1, 512), (4, 512)], ids=["2x128", "1x256", "1x512", "c2_4x512"])
 def test_vae_encode_and_backward_match_restatement(vae, B, res):
     vae_ref, sd32, sd16, enc = vae
     x, n, gl = _inputs(B, res)
@@ -109,8 +118,8 @@ def test_vae_encode_and_backward_match_restatement(vae, B, res):
     e_f, e_f16 = rel(lat, lat32), rel(lat16.float(), lat32)
     e_b, e_b16 = rel(gx, gx32), rel(gx16.float(), gx32)
     print(f"res {res} B {B}: latents rel err ours {e_f:.3e} (torch fp16 {e_f16:.3e}); d/dimage ours {e_b:.3e} (torch fp16 {e_b16:.3e})")
-    assert e_f < max(1e-3, 1.5 * e_f16)
-    assert e_b < max(1e-3, 1.5 * e_b16)
+    assert e_f < LAT_TOL
+    assert e_b < GRAD_TOL
 
 
 def test_vae_backward_is_linear_and_deterministic(vae):
@@ -156,6 +165,63 @@ def test_autograd_and_diffusers_surface(vae):
     print(f"diffusers surface: latents {e_lat:.3e}, d/dimage {e_grad:.3e} vs the fused entry point (same noise)")
     assert e_lat < 5e-3          # fp16 rounding of the [-1,1] image and of the sample before the scaling
     assert e_grad < 2e-2 and torch.isfinite(xr2.grad).all()
+
+
+def test_guidance_call_value_matches_fp32_restatement(vae):
+    """a10 by value: StableDiffusionGuidance.__call__ (stable_diffusion_guidance.py:374-448) -- permute,
+    bilinear resize to 512^2, encode_images, t ~ randint, compute_grad_sds, nan_to_num, clamp, the
+    0.5 * mse(latents, (latents - grad).detach(), 'sum') / B target trick -- against an fp32 restatement
+    with the same random draws. The UNet is a deterministic stand-in (eps = 0.1 x + 0.05 ctx-mean) so
+    that the comparison isolates __call__ and the VAE; the real UNet is covered by test_unet_gpu.py."""
+    from types import SimpleNamespace
+    import torch.nn.functional as F
+    from garmentdreamer_b200.guidance import PromptProcessorOutput, StableDiffusionGuidance
+    vae_ref, sd32, sd16, enc = vae
+
+    class TinyUNet:
+        def __call__(self, x, t, encoder_hidden_states=None):
+            c = encoder_hidden_states.float().mean(dim=(1, 2)).view(-1, 1, 1, 1)
+            return SimpleNamespace(sample=(0.1 * x.float() + 0.05 * c).to(x.dtype))
+
+    g = torch.Generator().manual_seed(3)
+    bank = lambda k: torch.randn(k, 77, 1024, generator=g).cuda()
+    pu = PromptProcessorOutput(bank(1), bank(1), bank(4), bank(4))
+    B = 2
+    elev, azim, dist = torch.tensor([10.0, 70.0]).cuda(), torch.tensor([20.0, 100.0]).cuda(), torch.tensor([2.0, 3.0]).cuda()
+    rgb = torch.rand(B, 256, 256, 3, generator=g).cuda()
+    for clip in (None, 0.05):
+        guide = StableDiffusionGuidance(TinyUNet(), "cuda", vae=enc, generator=torch.Generator(device="cuda").manual_seed(5))
+        guide.grad_clip_val = clip
+        x1 = rgb.clone().requires_grad_(True)
+        out = guide(x1, pu, elev, azim, dist)
+        out["loss_sds"].backward()
+        # ---- fp32 restatement with the same draws (encode noise, t, SDS noise: in this order) ----
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        x2 = rgb.clone().requires_grad_(True)
+        img = F.interpolate(x2.permute(0, 3, 1, 2), (512, 512), mode="bilinear", align_corners=False)
+        n_enc = torch.randn((B, 4, 64, 64), device="cuda", dtype=torch.float32, generator=gen)
+        lat = vae_ref.encode_images(sd32, img, n_enc)
+        t = torch.randint(guide.min_step, guide.max_step + 1, [B], dtype=torch.long, device="cuda", generator=gen)
+        noise = torch.randn(lat.shape, generator=gen, device="cuda", dtype=torch.float32)
+        a = guide.alphas[t].view(-1, 1, 1, 1)
+        with torch.no_grad():
+            noisy = a.sqrt() * lat + (1 - a).sqrt() * noise
+            emb = pu.get_text_embeddings(elev, azim, dist, True)
+            eps = TinyUNet()(torch.cat([noisy] * 2).half(), None, encoder_hidden_states=emb.half()).sample.float()
+            e_t, e_u = eps.chunk(2)
+            grad = (1 - a) * (e_t + 100.0 * (e_t - e_u) - noise)
+            grad = torch.nan_to_num(grad)
+            if clip is not None:
+                grad = grad.clamp(-clip, clip)
+        loss = 0.5 * F.mse_loss(lat, (lat - grad).detach(), reduction="sum") / B
+        loss.backward()
+        e_loss = abs(float(out["loss_sds"].detach()) - float(loss.detach())) / abs(float(loss.detach()))
+        e_norm = abs(float(out["grad_norm"]) - float(grad.norm())) / float(grad.norm())
+        e_grad = rel(x1.grad, x2.grad)
+        print(f"clip {clip}: loss {float(out['loss_sds'].detach()):.6g} vs {float(loss.detach()):.6g} (rel {e_loss:.2e}); grad_norm rel {e_norm:.2e}; d loss/d rgb rel {e_grad:.2e}")
+        assert out["min_step"] == 20 and out["max_step"] == 980
+        assert e_loss < 5e-3 and e_norm < 5e-3      # 2 x the latent tolerance (loss is quadratic in grad ~ latents)
+        assert e_grad < 2 * GRAD_TOL
 
 
 def test_guidance_call_differentiates_through_native_vae(vae):
