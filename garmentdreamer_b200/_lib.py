@@ -26,6 +26,7 @@ class GdCounters(ctypes.Structure):
         ("view_base", ctypes.c_uint32 * (GD_MAX_VIEWS + 1)),
         ("bwd_items", ctypes.c_uint32),
         ("bwd_next", ctypes.c_uint32),
+        ("depth_max_bits", ctypes.c_uint32),
     ]
 
 

@@ -104,6 +104,78 @@ k_densify_stats(int P, int B, const float* __restrict__ dmeans2D_sum, const int*
   max_radii2D[i] = fmaxf(max_radii2D[i], (float)r);
 }
 
+// ---- sparsity loss on the depth-normalised opacity -----------------------
+// Reference behaviour: TS/systems/GaussianDreamer.py:215 (opacity = depths / (depths.max() + 1e-5)) and
+// :253-255 (loss_sparsity = mean(sqrt(opacity^2 + 0.01))), differentiated by autograd into the depth
+// images. Pass 1: elementwise gradient + per-block partial sums (fixed order); pass 2 (one block): total;
+// pass 3: the term that flows through depths.max() lands on the arg-max pixel(s).
+__global__ void __launch_bounds__(256)
+k_sparsity_grad(long long n, float inv_ntotal, const float* __restrict__ depth, const float* __restrict__ depth_max,
+                float lambda, float* __restrict__ dL_ddepth, float* __restrict__ scratch) {
+  __shared__ float s_red[3][8];
+  const float dmax = *depth_max, inv = 1.0f / (dmax + 1e-5f);
+  float a = 0.f, bsum = 0.f, c = 0.f;
+  const long long base = (long long)blockIdx.x * 1024;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < n) {
+      const float d = depth[i], op = d * inv;
+      const float f = sqrtf(op * op + 0.01f);
+      const float g = lambda * inv_ntotal * op / f;     // dL/d opacity_i
+      dL_ddepth[i] = g * inv;
+      a += f; bsum += g * d; c += (d == dmax) ? 1.0f : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(~0u, a, o); bsum += __shfl_xor_sync(~0u, bsum, o); c += __shfl_xor_sync(~0u, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = a; s_red[1][threadIdx.x >> 5] = bsum; s_red[2][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += s_red[threadIdx.x][w];
+    scratch[3 * (size_t)blockIdx.x + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_sparsity_sum(int nblk, const float* __restrict__ scratch, float* __restrict__ stats) {
+  __shared__ double s_red[3][256];
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int k = threadIdx.x; k < nblk; k += 256)
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[j] += (double)scratch[3 * (size_t)k + j];
+#pragma unroll
+  for (int j = 0; j < 3; j++) s_red[j][threadIdx.x] = t[j];
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o)
+#pragma unroll
+      for (int j = 0; j < 3; j++) s_red[j][threadIdx.x] += s_red[j][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) stats[threadIdx.x] = (float)s_red[threadIdx.x][0];
+}
+__global__ void __launch_bounds__(256)
+k_sparsity_finish(long long n, float inv_ntotal, const float* __restrict__ depth, const float* __restrict__ depth_max,
+                  float lambda, const float* __restrict__ stats, float* __restrict__ dL_ddepth, float* __restrict__ loss_out) {
+  const float dmax = *depth_max, inv = 1.0f / (dmax + 1e-5f);
+  const float corr = -stats[1] * inv * inv / fmaxf(stats[2], 1.0f);
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i == 0 && loss_out) loss_out[0] = lambda * stats[0] * inv_ntotal;
+  if (i < n && depth[i] == dmax) dL_ddepth[i] += corr;
+}
+__global__ void __launch_bounds__(256)
+k_radii_max(int P, int B, const int* __restrict__ radii, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  int r = radii[i];
+  for (int b = 1; b < B; b++) r = max(r, radii[(size_t)b * P + i]);
+  out[i] = r;
+}
+
 // ---- batched camera construction ----------------------------------------
 // Reference behaviour: GS/scene/cameras.py:50-53 + GS/utils/graphics_utils.py:59-101, evaluated on
 // the CPU per view per iteration (two 4x4 LU inversions, two H2D copies, a GPU 4x4 inverse). Here:

@@ -253,6 +253,36 @@ int gd_densify_stats(int P, int B, const float* dmeans2D_sum, const int* radii, 
   return GD_OK;
 }
 
+int gd_sparsity_grad(long long n, long long n_total, const float* depth, const float* depth_max, float lambda,
+                     float* dL_ddepth, float* scratch, float* stats, gd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n < 1 || n_total < n || !depth || !depth_max || !dL_ddepth || !scratch || !stats)
+    return fail(GD_ERR_INVALID_ARG, "sparsity_grad: null pointer or bad element count%s");
+  const int nblk = (int)((n + 1023) / 1024);
+  gd::k_sparsity_grad<<<nblk, 256, 0, stream>>>(n, 1.0f / (float)n_total, depth, depth_max, lambda, dL_ddepth, scratch);
+  GD_LAUNCH_CHECK("k_sparsity_grad");
+  gd::k_sparsity_sum<<<1, 256, 0, stream>>>(nblk, scratch, stats);
+  GD_LAUNCH_CHECK("k_sparsity_sum");
+  return GD_OK;
+}
+int gd_sparsity_finish(long long n, long long n_total, const float* depth, const float* depth_max, float lambda,
+                       const float* stats, float* dL_ddepth, float* loss_out, gd_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n < 1 || n_total < n || !depth || !depth_max || !dL_ddepth || !stats)
+    return fail(GD_ERR_INVALID_ARG, "sparsity_finish: null pointer or bad element count%s");
+  gd::k_sparsity_finish<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, 1.0f / (float)n_total, depth, depth_max, lambda, stats,
+                                                                        dL_ddepth, loss_out);
+  GD_LAUNCH_CHECK("k_sparsity_finish");
+  return GD_OK;
+}
+int gd_radii_max(int P, int B, const int* radii, int* out, gd_stream_t stream) {
+  if (P < 0 || B < 1 || (P > 0 && (!radii || !out))) return fail(GD_ERR_INVALID_ARG, "radii_max: null pointer%s");
+  if (P == 0) return GD_OK;
+  gd::k_radii_max<<<(P + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, B, radii, out);
+  GD_LAUNCH_CHECK("k_radii_max");
+  return GD_OK;
+}
+
 int gd_cameras_from_c2w(int B, const float* c2w, const float* tan_half_fovx, const float* tan_half_fovy, float znear, float zfar,
                         float* out35, gd_stream_t stream) {
   if (B < 1 || B > GD_MAX_VIEWS) return fail(GD_ERR_INVALID_ARG, "cameras_from_c2w: B must be in 1..GD_MAX_VIEWS%s");

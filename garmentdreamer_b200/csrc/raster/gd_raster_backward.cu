@@ -549,7 +549,8 @@ k_bwd_epilogue(int P, int D, int M, int B, int W, int H, const float* __restrict
 #pragma unroll
     for (int k = 0; k < 3; k++) put(out.dL_dmeans3D, 3 * o1 + k, dmean[k], acc);
     if (scales) {  // cov3D -> scale / rotation (reference computeCov3D backward)
-      const float4 q = reinterpret_cast<const float4*>(rotations)[i];
+      // scalar loads: a caller may pass a slice of a packed buffer that is only 4-byte aligned
+      const float4 q = make_float4(rotations[4 * (size_t)i], rotations[4 * (size_t)i + 1], rotations[4 * (size_t)i + 2], rotations[4 * (size_t)i + 3]);
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       Mat3 R = {{{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
                  {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},

@@ -167,7 +167,8 @@ k_preprocess(int P, int D, int M, int B, int W, int H, int gx, int gy,
 #pragma unroll
       for (int k = 0; k < 6; k++) c3[k] = cov3D_precomp[6 * (size_t)i + k];
     } else {
-      const float4 q = reinterpret_cast<const float4*>(rotations)[i];
+      // scalar loads: a caller may pass a slice of a packed buffer that is only 4-byte aligned
+      const float4 q = make_float4(rotations[4 * (size_t)i], rotations[4 * (size_t)i + 1], rotations[4 * (size_t)i + 2], rotations[4 * (size_t)i + 3]);
       cov3d_from_scale_rot(scales[3 * (size_t)i], scales[3 * (size_t)i + 1],
                            scales[3 * (size_t)i + 2], mod, q, c3);
 #pragma unroll
@@ -318,6 +319,7 @@ k_spine(int nblk, uint32_t* __restrict__ scan_partials, int BT, int T, int B,
     counters->view_base[B] = total;
     counters->bwd_items = 0u;   // the forward compositor queues the backward work items
     counters->bwd_next = 0u;
+    counters->depth_max_bits = 0u;
   }
   // checkpoint slots: a tile with c instances has (c-1)/kSeg interior segment boundaries
   for (int k = threadIdx.x; k < BT; k += blockDim.x) {
@@ -636,7 +638,9 @@ k_render_fwd(int W, int H, int gx, int T, const uint32_t* __restrict__ ranges,
   }
   if (n > 0) {   // queue the tile's backward work items: one per kSeg records that were blended (at least one)
     const uint32_t wm = __reduce_max_sync(0xffffffffu, last_contributor);
-    if (lane == 0) s_max[warp] = wm;
+    // depth image maximum over the view batch (the depths are >= 0, so their IEEE bits order like integers)
+    const uint32_t dm = __reduce_max_sync(0xffffffffu, inside ? __float_as_uint(fmaxf(Dp, 0.0f)) : 0u);
+    if (lane == 0) { s_max[warp] = wm; if (dm) atomicMax(&counters->depth_max_bits, dm); }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t mx = 0;

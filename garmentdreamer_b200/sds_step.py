@@ -35,9 +35,11 @@ class SdsBenchStep:
         if use_vae:
             from .unet_init import random_vae_state_dict
             from .vae import VAEEncoderB200
-            self.vae = VAEEncoderB200(random_vae_state_dict(seed, self.dev), self.dev)
+            self.vae_state_dict = random_vae_state_dict(seed, self.dev)
+            self.vae = VAEEncoderB200(self.vae_state_dict, self.dev)
         self._vae_ms = []
         sd = state_dict if state_dict is not None else _random_state_dict(seed, self.dev)
+        self.unet_state_dict = sd
         self.unet = UNetB200(sd, self.dev, use_cuda_graph=use_cuda_graph)
         g = torch.Generator().manual_seed(1234 + seed)
         bank = lambda n: torch.randn(n, 77, 1024, generator=g).to(self.dev)
@@ -50,8 +52,13 @@ class SdsBenchStep:
         self._unet_ms = []
         self.last_grad = None
 
-    def image_grad(self, color, cams):
-        """color [B,3,S,S] fp32 (rasteriser output) -> dL_sds/dcolor [B,3,S,S] fp32."""
+    def set_min_max_steps(self, min_step_percent=0.02, max_step_percent=0.98):
+        self.guidance.set_min_max_steps(min_step_percent, max_step_percent)
+
+    def image_grad(self, color, elevation, azimuth, distances, scale=None):
+        """color [B,3,S,S] fp32 (rasteriser output) -> dL_sds/dcolor [B,3,S,S] fp32 of
+        loss_sds = 0.5 * mse(latents, (latents - grad).detach(), 'sum') * scale (scale = 1/B by default:
+        stable_diffusion_guidance.py:427; sharded views pass 1/(B*world))."""
         B, _, H, W = color.shape
         L = ops.lib()
         stream = torch.cuda.current_stream().cuda_stream
@@ -65,9 +72,9 @@ class SdsBenchStep:
             ops._chk(L.gd_unet_pool_latents(color.data_ptr(), self.mix.data_ptr(), lat.data_ptr(), B, H, W, stream), "pool_latents")
         t = torch.randint(self.guidance.min_step, self.guidance.max_step + 1, [B], dtype=torch.long, device=color.device,
                           generator=self.gen)
-        elev = torch.tensor([c.elevation_deg for c in cams], device=color.device)
-        azim = torch.tensor([c.azimuth_deg for c in cams], device=color.device)
-        dist = torch.tensor([c.distance for c in cams], device=color.device)
+        to_dev = lambda x: torch.as_tensor(x, dtype=torch.float32).to(color.device, non_blocking=True)
+        elev, azim, dist = to_dev(elevation), to_dev(azimuth), to_dev(distances)
+        scale = 1.0 / B if scale is None else float(scale)
         ev[1].record()
         grad, _ = self.guidance.compute_grad_sds(lat, t, self.prompt, elev, azim, dist)
         ev[2].record()
@@ -75,10 +82,10 @@ class SdsBenchStep:
         self.last_grad = grad
         clip = float(self.guidance.grad_clip_val or 0.0)
         if self.vae is not None:
-            dcol = self.vae.backward(grad, clip=clip, scale=1.0 / B)
+            dcol = self.vae.backward(grad, clip=clip, scale=scale)
         else:
             dcol = torch.empty_like(color)
-            ops._chk(L.gd_unet_pool_latents_bwd(grad.data_ptr(), self.mix.data_ptr(), dcol.data_ptr(), B, H, W, clip, 1.0 / B,
+            ops._chk(L.gd_unet_pool_latents_bwd(grad.data_ptr(), self.mix.data_ptr(), dcol.data_ptr(), B, H, W, clip, scale,
                                                 stream), "pool_latents_bwd")
         ev[3].record()
         self._vae_ms.append((ev[0], ev[1], ev[2], ev[3]))

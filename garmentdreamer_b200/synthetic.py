@@ -68,6 +68,7 @@ class CameraSample:
     azimuth_deg: float
     distance: float
     fovy: float
+    c2w: torch.Tensor = None   # [4,4] camera-to-world (batch['c2w_3dgs'] of the reference data module)
 
 
 def _projection(znear, zfar, fovx, fovy):
@@ -97,7 +98,7 @@ def camera_from_c2w(c2w: torch.Tensor, fovy: float, height: int, width: int, **m
     campos = wvt.inverse()[3, :3].float().contiguous()
     return CameraSample(wvt, full, campos, math.tan(fovx * 0.5), math.tan(fovy * 0.5),
                         meta.get("elevation_deg", 0.0), meta.get("azimuth_deg", 0.0),
-                        meta.get("distance", 0.0), fovy)
+                        meta.get("distance", 0.0), fovy, c2w.float().contiguous())
 
 
 def sample_cameras(B: int, height: int, width: int, seed: int = 123,
@@ -129,3 +130,22 @@ def sample_cameras(B: int, height: int, width: int, seed: int = 123,
                                     elevation_deg=float(elevation_deg[i]),
                                     azimuth_deg=float(azimuth_deg[i]), distance=float(dist[i])))
     return cams
+
+
+def sample_batch(B: int, height: int, width: int, seed: int = 123, lo: int = 0, hi: int = None):
+    """The training batch dict of the reference data module (threestudio/data/uncond.py:190-408) for the
+    cameras [lo, hi) of a B-view batch: c2w_3dgs [b,4,4], fovy [b] (radians), elevation / azimuth (degrees),
+    camera_distances, height, width -- host tensors, as a DataLoader worker would hand them over."""
+    cams = sample_cameras(B, height, width, seed)[lo:hi]
+    f = lambda xs: torch.tensor(xs, dtype=torch.float32)
+    return {"c2w_3dgs": torch.stack([c.c2w for c in cams]), "fovy": f([c.fovy for c in cams]),
+            "elevation": f([c.elevation_deg for c in cams]), "azimuth": f([c.azimuth_deg for c in cams]),
+            "camera_distances": f([c.distance for c in cams]), "height": height, "width": width}
+
+
+def raw_params(g):
+    """Inverse activations of garment(): raw xyz, f_dc, opacity (logit), scaling (log), rotation as stored by the
+    reference GaussianModel (scene/gaussian_model.py:41-50)."""
+    op = g["opacity"].clamp(1e-6, 1 - 1e-6)
+    return {"xyz": g["xyz"], "f_dc": g["shs"], "opacity": torch.log(op / (1 - op)), "scaling": torch.log(g["scales"]),
+            "rotation": g["rotations"]}

@@ -68,6 +68,8 @@ typedef struct {
   uint32_t view_base[GD_MAX_VIEWS + 1]; /* first instance of each view in the global list */
   uint32_t bwd_items;    /* backward work items (tile, list segment) queued by the forward compositor */
   uint32_t bwd_next;     /* next item to hand out; reset by every gd_raster_backward call */
+  uint32_t depth_max_bits; /* IEEE bits of max over the B depth images (>= 0): `depths.max()` of
+                              TS/systems/GaussianDreamer.py:215 without another pass over the images */
 } GdCounters;
 
 typedef struct {
@@ -186,6 +188,25 @@ int gd_params_adam(int P, float* xyz, float* f_dc, float* opacity, float* scalin
                    float beta1, float beta2, float eps, int step, gd_stream_t stream);
 int gd_densify_stats(int P, int B, const float* dmeans2D_sum, const int* radii, float* xyz_gradient_accum,
                      float* denom, float* max_radii2D, gd_stream_t stream);
+
+/* Sparsity loss on the depth-normalised opacity and its gradient w.r.t. the depth images:
+ *   opacity = depths / (depths.max() + 1e-5)                  TS/systems/GaussianDreamer.py:215
+ *   loss    = lambda * mean(sqrt(opacity^2 + 0.01))            :253-255 (mean over n_total elements)
+ * depth: DEVICE fp32 [n] (all B views of this rank, n = B*H*W); depth_max: DEVICE fp32 scalar holding the
+ * max over the WHOLE view batch (GdCounters.depth_max_bits reinterpreted, after an all-reduce MAX when the
+ * views are sharded over ranks); n_total = elements of the whole batch (all ranks).
+ * gd_sparsity_grad writes dL_ddepth [n] WITHOUT the term through depths.max() and the three partial sums
+ *   stats[0] = sum sqrt(op^2+0.01), stats[1] = sum_pix g_pix * depth_pix, stats[2] = #pixels == max
+ * (fixed summation order; sharded views: all-reduce SUM stats before the next call).
+ * gd_sparsity_finish adds the max() term, -stats[1] / (max+1e-5)^2 / stats[2] (autograd spreads it evenly
+ * over ties), to the arg-max pixels and writes loss_out[0] = lambda * stats[0] / n_total.
+ * scratch: DEVICE fp32 [3 * ceil(n / 1024)]. */
+int gd_sparsity_grad(long long n, long long n_total, const float* depth, const float* depth_max, float lambda,
+                     float* dL_ddepth, float* scratch, float* stats, gd_stream_t stream);
+int gd_sparsity_finish(long long n, long long n_total, const float* depth, const float* depth_max, float lambda,
+                       const float* stats, float* dL_ddepth, float* loss_out, gd_stream_t stream);
+/* out[i] = max over the B views of radii[b][i] (visibility / max_radii2D bookkeeping of a view batch) */
+int gd_radii_max(int P, int B, const int* radii, int* out, gd_stream_t stream);
 
 /* Batched camera construction: replaces Camera.__init__ (GS/scene/cameras.py:50-53,
  * GS/utils/graphics_utils.py:59-101), which the reference runs on the CPU per view per iteration.
