@@ -39,7 +39,7 @@ def test_camera_intrinsics_match_reference_formulas():
 
 def test_bench_line_contract_on_committed_run():
     """The JSON line of the last measured run (profiles/) carries every key the contract names."""
-    path = os.path.join(ROOT, "profiles", "r01_s9_bench.json")
+    path = os.path.join(ROOT, "profiles", "r02_b2_bench.json")
     d = json.load(open(path))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
@@ -56,3 +56,9 @@ def test_bench_line_contract_on_committed_run():
     assert any(k["traffic"] for k in r["dominant_kernels"])
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert math.isclose(d["value"], d["n_gpus"] * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3), rel_tol=1e-6)
+    # round 2: the step is the reference's whole iteration, with a same-run GPU reference block
+    assert set(d["phase_ms"]) == {"raster_fwd", "sparsity", "guidance", "raster_bwd", "allreduce", "adam"}
+    assert set(d["gpu_reference"]) >= {"raster_fwd_ms", "raster_bwd_ms", "unet_fp16_eager_ms", "vae_fp16_eager_autograd_ms", "ms_per_step"}
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r02_b2_bench_reference.json")))
+    assert ref["impl"] == "reference" and ref["extrapolated"] is True and ref["config"]["workload"] == d["config"]["workload"]
+    assert ref["cpu_baseline"]["kind"] == "port" and ref["e2e"]["h2d_bytes_per_step"] == 0
