@@ -23,10 +23,22 @@ from garmentdreamer_b200.raster import View, rasterize_views  # noqa: F401  (bat
 class _NativeShim:
     """``_C``-shaped facade: rasterize_gaussians / rasterize_gaussians_backward / mark_visible."""
 
-    _MAX_LIVE = 256
+    # Raw `_C` callers (the reference's pybind usage) look their state up by the geomBuffer they got back; the
+    # autograd Function below takes the entry out right after the forward and keeps it on its ctx, so forwards
+    # under no_grad (validation, the 120 test views, markVisible loops) hold nothing and a second backward
+    # (retain_graph=True) still finds its state.
+    _MAX_LIVE = 8
 
     def __init__(self):
         self._states = OrderedDict()  # geomBuffer.data_ptr() -> RasterState
+
+    def take_state(self, geomBuffer):
+        return self._states.pop(geomBuffer.data_ptr(), None)
+
+    def put_state(self, state):
+        self._states[state.geom.data_ptr()] = state
+        while len(self._states) > self._MAX_LIVE:
+            self._states.popitem(last=False)
 
     def rasterize_gaussians(self, bg, means3D, colors, opacity, scales, rotations, scale_modifier,
                             cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
@@ -37,9 +49,7 @@ class _NativeShim:
             colors_precomp=colors, scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp,
             scale_modifier=scale_modifier, sh_degree=degree, prefiltered=prefiltered, debug=debug,
             sync=True)
-        self._states[state.geom.data_ptr()] = state
-        while len(self._states) > self._MAX_LIVE:
-            self._states.popitem(last=False)
+        self.put_state(state)
         return (state.num_rendered, color[0], depth[0], alpha[0], radii[0], state.geom,
                 state.binning, state.img)
 
@@ -48,7 +58,7 @@ class _NativeShim:
                                      tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth,
                                      dL_dout_alpha, sh, degree, campos, geomBuffer, R,
                                      binningBuffer, imageBuffer, alphas, debug):
-        state = self._states.pop(geomBuffer.data_ptr(), None)
+        state = self._states.get(geomBuffer.data_ptr())
         if state is None or state.binning.data_ptr() != binningBuffer.data_ptr():
             raise RuntimeError("rasterize_gaussians_backward: unknown state buffers (they must be "
                                "the ones returned by rasterize_gaussians)")
@@ -116,6 +126,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         else:
             out = _C.rasterize_gaussians(*args)
         num_rendered, color, depth, alpha, radii, geomBuffer, binningBuffer, imgBuffer = out
+        state = _C.take_state(geomBuffer)          # owned by this graph node from here on (nothing global stays alive)
+        ctx.gd_state = state if any(ctx.needs_input_grad) else None
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
@@ -139,6 +151,17 @@ class _RasterizeGaussians(torch.autograd.Function):
                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_color,
                 grad_depth, grad_alpha, sh, rs.sh_degree, rs.campos, geomBuffer, num_rendered,
                 binningBuffer, imgBuffer, alpha, rs.debug)
+        if ctx.gd_state is None:
+            raise RuntimeError("rasterize_gaussians: backward called on a forward that needed no gradient")
+        _C.put_state(ctx.gd_state)                 # visible to the _C-shaped entry point for the duration of the call
+        try:
+            return _RasterizeGaussians._backward_impl(ctx, args, colors_precomp, scales, rotations, cov3Ds_precomp, sh)
+        finally:
+            _C.take_state(geomBuffer)
+
+    @staticmethod
+    def _backward_impl(ctx, args, colors_precomp, scales, rotations, cov3Ds_precomp, sh):
+        rs = ctx.raster_settings
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
