@@ -79,6 +79,38 @@ template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   launch_pdl_cluster(1, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
+// ---- per-device scratch (split-K partials, GroupNorm partial statistics) ------------------------------
+// One set per CUDA device, allocated on first use ON THAT DEVICE (or up front by gd_unet_init, which callers
+// that capture CUDA graphs run before the capture: cudaMalloc is illegal inside one). The buffers are shared by
+// every stream of the device: the library serves ONE stream per device at a time (documented in gd_unet.h).
+struct DeviceScratch {
+  float* splitk_ws = nullptr;        // [kSplitKFloats]
+  float2* gn_part_small = nullptr;   // [kGnSmall]   gd_unet_groupnorm
+  float2* gn_part = nullptr;         // [kGnBig]     gd_unet_groupnorm_stats / _bwd
+  float2* gn_bstats = nullptr;       // [8192]
+};
+constexpr size_t kSplitKFloats = (size_t)24 << 20;   // 96 MB
+constexpr size_t kGnSmall = (size_t)4096 * 64, kGnBig = (size_t)8192 * 512;
+constexpr int kMaxDevices = 64;
+DeviceScratch g_scratch[kMaxDevices];
+DeviceScratch* device_scratch() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  DeviceScratch& s = g_scratch[dev];
+  if (!s.splitk_ws) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    (void)cap;
+    if (cudaMalloc(&s.splitk_ws, kSplitKFloats * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&s.gn_part_small, kGnSmall * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc(&s.gn_part, kGnBig * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc(&s.gn_bstats, 8192 * sizeof(float2)) != cudaSuccess) {
+      cudaGetLastError();
+      s = DeviceScratch();
+      return nullptr;
+    }
+  }
+  return &s;
+}
 #define LAUNCH_CHECK(what)              \
   do {                                  \
     const int rc_ = check_launch(what); \
@@ -623,7 +655,10 @@ extern "C" {
 const char* gd_unet_last_error(void) { return g_err; }
 uint64_t gd_unet_launch_count(void) { return g_launches.load(); }
 uint64_t gd_unet_pair_launch_count(void) { return g_pair_launches.load(); }
-const char* gd_unet_version(void) { return "gd_unet 0.1 (sm_100a, tcgen05+TMA)"; }
+const char* gd_unet_version(void) { return "gd_unet 0.2 (sm_100a, tcgen05+TMA)"; }
+int gd_unet_init(void) {   // allocate the current device's scratch now (call before capturing a CUDA graph)
+  return device_scratch() ? GD_UNET_OK : fail(GD_UNET_ERR_CUDA, "init: per-device scratch allocation failed");
+}
 
 int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -681,7 +716,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
       int ks = (int)(148 / tiles);
       if (ks > num_kb_all / 6) ks = num_kb_all / 6;
       if (ks > 16) ks = 16;
-      if (ks >= 2 && (size_t)ks * a->M * a->N <= ((size_t)24 << 20)) ksplit = ks;
+      if (ks >= 2 && (size_t)ks * a->M * a->N <= kSplitKFloats) ksplit = ks;
     }
   }
   // CTA pairs (cta_group::2): every GEMM with at least two M tiles per batch entry
@@ -766,10 +801,10 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.n_tiles = n_tiles_all;
   p.ksplit = 1; p.kb_per_split = p.num_kb; p.ws = nullptr;
   // split-K partials in fp32, summed in a fixed order by k_splitk_finalize (deterministic)
-  static float* ws = nullptr;
-  const size_t ws_floats = (size_t)24 << 20;  // 96 MB
   if (ksplit > 1) {
-    if (!ws && cudaMalloc(&ws, ws_floats * sizeof(float)) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "gemm: split-K workspace");
+    DeviceScratch* sc = device_scratch();
+    if (!sc) return fail(GD_UNET_ERR_CUDA, "gemm: split-K workspace (per-device scratch allocation failed)");
+    float* ws = sc->splitk_ws;
     p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
     p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
     p.ws = ws;
@@ -893,12 +928,14 @@ int gd_unet_groupnorm(const void* x, void* y, const void* gamma, const void* bet
     return GD_UNET_OK;
   }
   // partial statistics live in a small static device buffer (N*groups*splits float2 <= 512 KB)
-  static float2* part = nullptr;
-  if (!part && cudaMalloc(&part, sizeof(float2) * 4096 * 64) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm: cudaMalloc");
+  DeviceScratch* sc = device_scratch();
+  if (!sc) return fail(GD_UNET_ERR_CUDA, "groupnorm: per-device scratch allocation failed");
+  float2* part = sc->gn_part_small;
   int splits = (HW * (C / 8) + 8191) / 8192;  // ~32 sixteen-byte loads per thread
   if (splits > 16) splits = 16;
   if (splits < 1) splits = 1;
   while (N * splits < 296 && splits < 64 && HW / (splits * 2) >= 16) splits *= 2;  // at least ~2 CTAs per SM
+  if ((size_t)N * groups * splits > kGnSmall) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm: N * groups * splits exceeds the partial-statistics scratch");
   launch_pdl(gdu::k_gn_stats, dim3(dim3(N, splits)), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), (const __half*)x, part, HW, C, groups, splits);
   LAUNCH_CHECK("k_gn_stats");
   int pix_per_cta = (int)((16384 + C - 1) / C);  // ~16k elements per CTA
@@ -1007,10 +1044,9 @@ int gd_unet_pool_latents_bwd(const float* grad, const float* mix, float* dcolor,
 }
 // ---- VAE encoder support (include/gd_unet.h, "VAE" section) -----------------------------------
 namespace {
-float2* gn_part_buffer() {   // partial statistics: up to 8192 (image, group) x 512 splits
-  static float2* part = nullptr;
-  if (!part && cudaMalloc(&part, sizeof(float2) * 8192 * 512) != cudaSuccess) return nullptr;
-  return part;
+float2* gn_part_buffer() {   // partial statistics: up to 8192 (image, group) x 512 splits, per device
+  DeviceScratch* sc = device_scratch();
+  return sc ? sc->gn_part : nullptr;
 }
 // pixels per CTA of the fast sweeps: up to 128 K elements per CTA, but at least ~600 CTAs
 int gn_fast_pix_per_cta(int N, int HW, int C, int unroll) {
@@ -1041,6 +1077,7 @@ int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const voi
   float2* part = gn_part_buffer();
   if (!part) return fail(GD_UNET_ERR_CUDA, "groupnorm_stats: cudaMalloc");
   const int splits = gn_big_splits(N, HW, C);
+  if ((size_t)N * groups * splits > kGnBig) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: N * groups * splits exceeds the scratch");
   launch_pdl(gdu::k_gn_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, part, HW, C, groups, splits);
   LAUNCH_CHECK("k_gn_stats");
   const int total = N * groups;
@@ -1077,9 +1114,9 @@ int gd_unet_groupnorm_bwd(const void* x, const void* dz, const void* add, void* 
     return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: C % groups == 0, C % 8 == 0, C <= 2048");
   float2* part = gn_part_buffer();
   if (!part) return fail(GD_UNET_ERR_CUDA, "groupnorm_bwd: cudaMalloc");
-  static float2* bstats = nullptr;
-  if (!bstats && cudaMalloc(&bstats, sizeof(float2) * 8192) != cudaSuccess) return fail(GD_UNET_ERR_CUDA, "groupnorm_bwd: cudaMalloc");
+  float2* bstats = device_scratch()->gn_bstats;
   const int splits = gn_big_splits(N, HW, C);
+  if ((size_t)N * groups * splits > kGnBig) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: N * groups * splits exceeds the scratch");
   launch_pdl(gdu::k_gn_bwd_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
              (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits, silu);
   LAUNCH_CHECK("k_gn_bwd_stats");
@@ -1141,10 +1178,22 @@ int gd_vae_im2col(const float* color, void* A, int B, int H, int W, float a, flo
   LAUNCH_CHECK("k_vae_im2col");
   return GD_UNET_OK;
 }
-int gd_vae_dimg_gather(const void* Z, float* dcolor, int B, int H, int W, float scale, gd_ustream_t s) {
+int gd_vae_dimg_gather_dyn(const void* Z, float* dcolor, int B, int H, int W, float scale, const float* dyn, gd_ustream_t s) {
   const long long n = (long long)B * H * W;
-  launch_pdl(gdu::k_vae_dimg_gather, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)Z, dcolor, B, H, W, scale);
+  launch_pdl(gdu::k_vae_dimg_gather, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)Z, dcolor, B, H, W, scale, dyn);
   LAUNCH_CHECK("k_vae_dimg_gather");
+  return GD_UNET_OK;
+}
+int gd_vae_dimg_gather(const void* Z, float* dcolor, int B, int H, int W, float scale, gd_ustream_t s) {
+  return gd_vae_dimg_gather_dyn(Z, dcolor, B, H, W, scale, nullptr, s);
+}
+int gd_vae_grad_scale(const float* grad, long long n, float clip, float pre, float target, float* scratch, float* dyn, gd_ustream_t s) {
+  if (!grad || n < 1 || !scratch || !dyn || !(target > 0.f)) return fail(GD_UNET_ERR_INVALID_ARG, "vae_grad_scale: bad argument");
+  const int nblk = (int)((n + 1023) / 1024);
+  launch_pdl(gdu::k_vae_grad_absmax, dim3(nblk), dim3(256), (size_t)0, (cudaStream_t)s, grad, n, clip, scratch);
+  LAUNCH_CHECK("k_vae_grad_absmax");
+  launch_pdl(gdu::k_vae_grad_scale, dim3(1), dim3(256), (size_t)0, (cudaStream_t)s, nblk, (const float*)scratch, pre, target, dyn);
+  LAUNCH_CHECK("k_vae_grad_scale");
   return GD_UNET_OK;
 }
 int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling, gd_ustream_t s) {
@@ -1154,9 +1203,13 @@ int gd_vae_sample(const void* moments, const float* noise, float* latents, int B
 }
 int gd_vae_sample_bwd(const float* grad, const void* moments, const float* noise, void* dmoments, int B, int hw, int Cp,
                       float scaling, float clip, float gscale, gd_ustream_t s) {
+  return gd_vae_sample_bwd_dyn(grad, moments, noise, dmoments, B, hw, Cp, scaling, clip, gscale, nullptr, s);
+}
+int gd_vae_sample_bwd_dyn(const float* grad, const void* moments, const float* noise, void* dmoments, int B, int hw, int Cp,
+                          float scaling, float clip, float gscale, const float* dyn, gd_ustream_t s) {
   if (Cp < 8 || Cp % 8) return fail(GD_UNET_ERR_INVALID_ARG, "vae_sample_bwd: Cp must be a multiple of 8, >= 8");
   launch_pdl(gdu::k_vae_sample_bwd, dim3((B * hw + 255) / 256), dim3(256), (size_t)0, (cudaStream_t)s, grad, (const __half*)moments, noise,
-             (__half*)dmoments, B, hw, Cp, scaling, clip, gscale);
+             (__half*)dmoments, B, hw, Cp, scaling, clip, gscale, dyn);
   LAUNCH_CHECK("k_vae_sample_bwd");
   return GD_UNET_OK;
 }

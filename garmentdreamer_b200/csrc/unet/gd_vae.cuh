@@ -393,10 +393,58 @@ __global__ void k_vae_sample(const __half* __restrict__ mom, const float* __rest
 // Backward of the sampler: grad fp32 NCHW [B,4,h,w] (nan_to_num + clamp(+-clip) applied here,
 // stable_diffusion_guidance.py:418-421) -> d moments fp16 NHWC [B,h,w,Cp] (8 real channels, the
 // rest zero so that the tensor is a valid K operand of the conv-GEMM). `gscale` = loss scale.
+// max |nan_to_num(clamp(g))| per 1024-element block, then the power-of-two loss scale (see gd_vae_grad_scale)
+__global__ void __launch_bounds__(256)
+k_vae_grad_absmax(const float* __restrict__ grad, long long n, float clip, float* __restrict__ scratch) {
+  pdl_entry();
+  __shared__ float s_w[8];
+  float m = 0.f;
+  const long long base = (long long)blockIdx.x * 1024;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < n) {
+      float g = grad[i];
+      if (!(g == g)) g = 0.f;
+      g = fminf(fabsf(g), 3.4028235e38f);
+      if (clip > 0.f) g = fminf(g, clip);
+      m = fmaxf(m, g);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(~0u, m, o));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; w++) m = fmaxf(m, s_w[w]);
+    scratch[blockIdx.x] = m;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_vae_grad_scale(int nblk, const float* __restrict__ scratch, float pre, float target, float* __restrict__ dyn) {
+  pdl_entry();
+  __shared__ float s_w[8];
+  float m = 0.f;
+  for (int k = threadIdx.x; k < nblk; k += 256) m = fmaxf(m, scratch[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(~0u, m, o));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; w++) m = fmaxf(m, s_w[w]);
+    const float top = m * fabsf(pre);
+    float e = 0.f;
+    if (top > 0.f && top < 3.0e38f) e = floorf(log2f(target / top));
+    *dyn = exp2f(fminf(fmaxf(e, -24.f), 24.f));
+  }
+}
 __global__ void k_vae_sample_bwd(const float* __restrict__ grad, const __half* __restrict__ mom,
                                  const float* __restrict__ noise, __half* __restrict__ dmom, int B, int hw, int Cp,
-                                 float scaling, float clip, float gscale) {
+                                 float scaling, float clip, float gscale, const float* __restrict__ dyn) {
   pdl_entry();
+  if (dyn) gscale *= *dyn;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * hw) return;
   const int p = i % hw, b = i / hw;
@@ -414,8 +462,9 @@ __global__ void k_vae_sample_bwd(const float* __restrict__ grad, const __half* _
     const float lv = __half2float(m[4 + k]);
     const bool inside = lv >= -30.0f && lv <= 20.0f;   // clamp passes gradient inside its range
     const float std_ = expf(0.5f * fminf(fmaxf(lv, -30.0f), 20.0f));
-    o[k] = __float2half_rn(g);
-    o[4 + k] = __float2half_rn(inside ? g * noise[gi] * 0.5f * std_ : 0.0f);
+    // saturate instead of overflowing to inf (fp16 max 65504): an inf here turns the whole chain into NaN
+    o[k] = __float2half_rn(fminf(fmaxf(g, -65504.f), 65504.f));
+    o[4 + k] = __float2half_rn(inside ? fminf(fmaxf(g * noise[gi] * 0.5f * std_, -65504.f), 65504.f) : 0.0f);
   }
   *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(o);
   for (int c = 8; c < Cp; c += 8) *reinterpret_cast<uint4*>(d + c) = make_uint4(0, 0, 0, 0);
@@ -459,8 +508,10 @@ k_vae_im2col(const float* __restrict__ color, __half* __restrict__ A, int B, int
 // ---- conv_in data gradient from the per-pixel tap products Z[(b,y,x), (ky*3+kx)*3+c] (fp16, 32 wide):
 // dcolor[b,c,y,x] = scale * sum_{ky,kx} Z[(b, y-ky+1, x-kx+1), (ky*3+kx)*3+c]
 __global__ void __launch_bounds__(256)
-k_vae_dimg_gather(const __half* __restrict__ Z, float* __restrict__ dcolor, int B, int H, int W, float scale) {
+k_vae_dimg_gather(const __half* __restrict__ Z, float* __restrict__ dcolor, int B, int H, int W, float scale,
+                  const float* __restrict__ dyn) {
   pdl_entry();
+  if (dyn) scale /= *dyn;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long HW = (long long)H * W;
   if (i >= (long long)B * HW) return;
@@ -477,7 +528,12 @@ k_vae_dimg_gather(const __half* __restrict__ Z, float* __restrict__ dcolor, int 
       for (int c = 0; c < 3; c++) acc[c] += __half2float(z[c]);
     }
   float* d = dcolor + (long long)b * 3 * HW + (long long)y * W + x;
-  d[0] = acc[0] * scale; d[HW] = acc[1] * scale; d[2 * HW] = acc[2] * scale;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float v = acc[c] * scale;
+    if (dyn && !(fabsf(v) <= 3.4028235e38f)) v = 0.f;   // NaN / inf out of an overflowed fp16 chain -> 0
+    d[c * HW] = v;
+  }
 }
 
 }  // namespace gdu

@@ -33,6 +33,7 @@ class UNetB200:
     def __init__(self, state_dict, device="cuda", use_cuda_graph=True):
         self.device = torch.device(device)
         ops.lib()  # fail loudly if the CUDA library is missing
+        ops.init_device(self.device)
         self.w = {}
         for k, v in state_dict.items():
             self.w[k] = self._convert(k, v)

@@ -84,14 +84,34 @@ def lib():
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
         L.gd_vae_im2col.argtypes = [vp, vp, i, i, i, f, f, vp]
         L.gd_vae_dimg_gather.argtypes = [vp, vp, i, i, i, f, vp]
+        L.gd_vae_dimg_gather_dyn.argtypes = [vp, vp, i, i, i, f, vp, vp]
+        L.gd_vae_grad_scale.argtypes = [vp, ll, f, f, f, vp, vp, vp]
+        L.gd_vae_sample_bwd_dyn.argtypes = [vp, vp, vp, vp, i, i, i, f, f, f, vp, vp]
+        for name in ("dimg_gather_dyn", "grad_scale", "sample_bwd_dyn"):
+            getattr(L, "gd_vae_" + name).restype = ctypes.c_int
         for name in ("prep", "sample", "sample_bwd", "dimg", "im2col", "dimg_gather"):
             getattr(L, "gd_vae_" + name).restype = ctypes.c_int
         for name in ("gemm", "flash_attn", "groupnorm", "layernorm", "softmax", "geglu", "add", "upsample2x", "space_to_depth",
                      "concat", "small_linear", "timestep_embedding", "conv_in", "conv_out", "add_noise", "sds_grad",
                      "pool_latents", "pool_latents_bwd"):
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
+        L.gd_unet_init.restype = ctypes.c_int
         _unet = L
     return _unet
+
+
+_inited = set()
+
+
+def init_device(device=None):
+    """Allocate the per-device scratch of libgd_unet.so for `device` (before any CUDA-graph capture)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx in _inited:
+        return
+    with torch.cuda.device(idx):
+        _chk(lib().gd_unet_init(), "gd_unet_init")
+    _inited.add(idx)
 
 
 def _stream():

@@ -23,7 +23,8 @@ from . import unet_ops as ops
 CH = (128, 256, 512, 512)
 SCALING = 0.18215
 EPS = 1e-6
-GRAD_SCALE = 256.0   # loss scale for the fp16 backward (power of two: exact; removed in gd_vae_dimg)
+GRAD_TARGET = 16.0   # the fp16 backward chain starts with max |d moments| in [8, 16): a power-of-two loss scale chosen
+                     # on the device from the incoming gradient (gd_vae_grad_scale), removed again in gd_vae_dimg_gather_dyn
 
 # stride-2 3x3 conv with padding (0,1,0,1) on the space-to-depth tensor: tap (ky,kx) reads phase
 # (ky&1, kx&1) at shift (ky>>1, kx>>1)
@@ -36,6 +37,7 @@ class VAEEncoderB200:
     def __init__(self, state_dict, device="cuda"):
         self.device = torch.device(device)
         ops.lib()  # fail loudly if the CUDA library is missing
+        ops.init_device(self.device)
         sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()}
         self.w = {}
         h = lambda t: t.to(torch.float16).contiguous()
@@ -232,8 +234,15 @@ class VAEEncoderB200:
         h, w_ = H // 8, W // 8
         g = grad_latents.detach().float().contiguous()
         dmom = torch.empty((B, h, w_, 64), dtype=torch.float16, device=g.device)
-        ops._chk(L.gd_vae_sample_bwd(g.data_ptr(), mom.data_ptr(), noise.data_ptr(), dmom.data_ptr(), B, h * w_, 64,
-                                     scaling, float(clip), GRAD_SCALE * float(scale), st), "vae_sample_bwd")
+        n = g.numel()
+        if getattr(self, "_dyn", None) is None:
+            self._dyn = torch.ones(1, dtype=torch.float32, device=g.device)
+        if getattr(self, "_dyn_scratch", None) is None or self._dyn_scratch.numel() < (n + 1023) // 1024:
+            self._dyn_scratch = torch.empty((n + 1023) // 1024, dtype=torch.float32, device=g.device)
+        ops._chk(L.gd_vae_grad_scale(g.data_ptr(), n, float(clip), scaling * float(scale), GRAD_TARGET, self._dyn_scratch.data_ptr(),
+                                     self._dyn.data_ptr(), st), "vae_grad_scale")
+        ops._chk(L.gd_vae_sample_bwd_dyn(g.data_ptr(), mom.data_ptr(), noise.data_ptr(), dmom.data_ptr(), B, h * w_, 64,
+                                         scaling, float(clip), float(scale), self._dyn.data_ptr(), st), "vae_sample_bwd")
         dn = ops.conv3x3(dmom, self.w["conv_out.bwd"])
         d = ops.groupnorm_bwd(x_out, dn, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"], stn, silu=True, out=dn)
         for rec in reversed(saved):
@@ -245,7 +254,7 @@ class VAEEncoderB200:
                 d = self._down_bwd(rec, d)
         z = ops.linear(d.view(B * H * W, -1), self.w["conv_in.bwd"])              # [B*H*W,32] per-pixel tap products
         dimg = torch.empty((B, 3, H, W), dtype=torch.float32, device=g.device)
-        ops._chk(L.gd_vae_dimg_gather(z.data_ptr(), dimg.data_ptr(), B, H, W, a / GRAD_SCALE, st), "vae_dimg_gather")
+        ops._chk(L.gd_vae_dimg_gather_dyn(z.data_ptr(), dimg.data_ptr(), B, H, W, a, self._dyn.data_ptr(), st), "vae_dimg_gather")
         return dimg
 
     # ---- autograd + the diffusers surface the reference calls ---------------------------------

@@ -166,6 +166,21 @@ int gd_vae_im2col(const float* color_nchw, void* A, int B, int H, int W, float a
    dcolor[b,c,y,x] = scale * sum_taps Z[(b, y-ky+1, x-kx+1), (ky*3+kx)*3+c]; fp32 NCHW out. */
 int gd_vae_dimg_gather(const void* Z, float* dcolor_nchw, int B, int H, int W, float scale,
                        gd_ustream_t stream);
+/* The same with the DYNAMIC loss scale of gd_vae_grad_scale removed (dcolor = scale / *dyn_scale * sum ...) and
+   non-finite results replaced by 0 (torch.nan_to_num(nan=0, posinf=0, neginf=0): an overflowed fp16 chain never
+   reaches the Gaussians' Adam state). */
+int gd_vae_dimg_gather_dyn(const void* Z, float* dcolor_nchw, int B, int H, int W, float scale,
+                           const float* dyn_scale, gd_ustream_t stream);
+/* Loss scale for the fp16 backward chain, chosen on the device from the gradient that enters it:
+   *dyn_scale = 2^floor(log2(target / max|nan_to_num(clamp(grad, +-clip)) * pre|)), clamped to [2^-24, 2^24], 1 when the
+   gradient is all zero. n = elements of grad; scratch: DEVICE fp32 [ceil(n/1024)]. With guidance scale 100 and
+   grad_clip = None (the reference's Config default) a fixed scale overflows fp16; a power of two is exact. */
+int gd_vae_grad_scale(const float* grad, long long n, float clip, float pre, float target, float* scratch,
+                      float* dyn_scale, gd_ustream_t stream);
+/* gd_vae_sample_bwd with that device-side scale as an extra factor. */
+int gd_vae_sample_bwd_dyn(const float* grad, const void* moments, const float* noise, void* dmoments, int B,
+                          int hw, int Cp, float scaling, float clip, float gscale, const float* dyn_scale,
+                          gd_ustream_t stream);
 /* DiagonalGaussianDistribution.sample() * scaling: moments fp16 NHWC [B,hw,8] (mean | logvar,
    logvar clamped to [-30,20]), noise fp32 NCHW [B,4,hw] -> latents fp32 NCHW [B,4,hw]. */
 int gd_vae_sample(const void* moments, const float* noise, float* latents, int B, int hw, float scaling,
@@ -192,6 +207,11 @@ uint64_t gd_unet_launch_count(void);
 /* GEMM launches so far that ran as CTA pairs (tcgen05 cta_group::2, clusters of 2). */
 uint64_t gd_unet_pair_launch_count(void);
 const char* gd_unet_version(void);
+/* Scratch (split-K partials 96 MB, GroupNorm partial statistics) is kept PER CUDA DEVICE and allocated on first
+ * use on that device; gd_unet_init() allocates the current device's set up front -- call it before capturing a
+ * CUDA graph (cudaMalloc is illegal during capture). The scratch is shared by all streams of a device: issue this
+ * library's calls from ONE stream per device at a time. */
+int gd_unet_init(void);
 
 #ifdef __cplusplus
 }

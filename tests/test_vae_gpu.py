@@ -140,6 +140,22 @@ def test_vae_backward_is_linear_and_deterministic(vae):
     assert torch.isfinite(g6).all()
 
 
+def test_vae_backward_unclipped_large_and_tiny_gradients(vae):
+    """grad_clip defaults to None in the reference's Config and guidance scale 100 makes |grad| large: the fp16 chain
+    carries a power-of-two loss scale chosen on the device from the incoming gradient, so the result stays finite and
+    linear over 12 orders of magnitude (a fixed scale of 256 overflows at ~1e3 and flushes to zero at ~1e-7)."""
+    vae_ref, sd32, sd16, enc = vae
+    x, n, gl = _inputs(1, 128, seed=11)
+    enc.encode(x, n); base = enc.backward(gl)
+    for k in (1e-6, 1e-3, 1e3, 1e6):
+        enc.encode(x, n); gk = enc.backward(gl * k)
+        assert torch.isfinite(gk).all()
+        assert rel(gk / k, base) < 2e-3, k
+    spike = gl.clone(); spike[0, 1, 3, 3] = 3.0e38; spike[0, 2, 5, 5] = float("inf")
+    enc.encode(x, n); gs = enc.backward(spike)
+    assert torch.isfinite(gs).all()
+
+
 def test_autograd_and_diffusers_surface(vae):
     """encode_images as a torch.autograd.Function, and the `vae.encode(x).latent_dist.sample()` /
     `vae.config.scaling_factor` surface the unmodified reference class calls (:165-166)."""
