@@ -1221,6 +1221,21 @@ int gd_vae_dimg(const void* dx, float* dcolor, int B, int H, int W, int Cp, floa
   return GD_UNET_OK;
 }
 
+int gd_resize_bilinear(const float* in, float* out, int BC, int Hi, int Wi, int Ho, int Wo, gd_ustream_t s) {
+  if (!in || !out || BC < 1 || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1) return fail(GD_UNET_ERR_INVALID_ARG, "resize_bilinear: bad argument");
+  const long long n = (long long)BC * Ho * Wo;
+  launch_pdl(gdu::k_resize_bilinear, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, in, out, BC, Hi, Wi, Ho, Wo);
+  LAUNCH_CHECK("k_resize_bilinear");
+  return GD_UNET_OK;
+}
+int gd_resize_bilinear_bwd(const float* dout, float* din, int BC, int Hi, int Wi, int Ho, int Wo, gd_ustream_t s) {
+  if (!dout || !din || BC < 1 || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1) return fail(GD_UNET_ERR_INVALID_ARG, "resize_bilinear_bwd: bad argument");
+  const long long n = (long long)BC * Hi * Wi;
+  launch_pdl(gdu::k_resize_bilinear_bwd, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, dout, din, BC, Hi, Wi, Ho, Wo);
+  LAUNCH_CHECK("k_resize_bilinear_bwd");
+  return GD_UNET_OK;
+}
+
 int gd_unet_sds_grad(const float* eps, const float* noise, const float* w, float gs, float* np, float* grad, int B, int chw,
                      gd_ustream_t s) {
   launch_pdl(gdu::k_sds_grad, dim3((B * chw + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)((cudaStream_t)s), eps, noise, w, gs, np, grad, B, chw);

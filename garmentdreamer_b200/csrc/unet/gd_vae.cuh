@@ -536,4 +536,58 @@ k_vae_dimg_gather(const __half* __restrict__ Z, float* __restrict__ dcolor, int 
   }
 }
 
+// ---- bilinear resize either side of the VAE ------------------------------------------
+// F.interpolate(rgb_BCHW, (512, 512), mode="bilinear", align_corners=False) of the reference guidance
+// (stable_diffusion_guidance.py:387-396; 1024^2 renders -> 512^2 in the shipped config) and its transpose for the
+// gradient. PyTorch's rule: src = max((dst + 0.5) * in/out - 0.5, 0), i0 = floor(src), i1 = min(i0 + 1, in - 1).
+__device__ __forceinline__ void bil_src(int d, float scale, int n_in, int& i0, int& i1, float& w1) {
+  const float sidx = fmaxf(((float)d + 0.5f) * scale - 0.5f, 0.0f);
+  i0 = min((int)sidx, n_in - 1);
+  i1 = min(i0 + 1, n_in - 1);
+  w1 = sidx - (float)i0;
+}
+__global__ void __launch_bounds__(256)
+k_resize_bilinear(const float* __restrict__ in, float* __restrict__ out, int BC, int Hi, int Wi, int Ho, int Wo) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)BC * Ho * Wo) return;
+  const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), bc = (int)(i / ((long long)Wo * Ho));
+  int y0, y1, x0, x1;
+  float wy, wx;
+  bil_src(y, (float)Hi / (float)Ho, Hi, y0, y1, wy);
+  bil_src(x, (float)Wi / (float)Wo, Wi, x0, x1, wx);
+  const float* p = in + (long long)bc * Hi * Wi;
+  const float v00 = p[(long long)y0 * Wi + x0], v01 = p[(long long)y0 * Wi + x1];
+  const float v10 = p[(long long)y1 * Wi + x0], v11 = p[(long long)y1 * Wi + x1];
+  out[i] = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
+}
+// Transpose as a GATHER (deterministic, no atomics): an input pixel sums the weights of the few output pixels whose
+// 2x2 footprint contains it.
+__global__ void __launch_bounds__(256)
+k_resize_bilinear_bwd(const float* __restrict__ dout, float* __restrict__ din, int BC, int Hi, int Wi, int Ho, int Wo) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)BC * Hi * Wi) return;
+  const int x = (int)(i % Wi), y = (int)((i / Wi) % Hi), bc = (int)(i / ((long long)Wi * Hi));
+  const float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+  // candidate outputs: src in (y - 1, y + 1)  <=>  dst in ((y - 0.5) / s - 0.5, (y + 1.5) / s - 0.5)
+  const int ya = max(0, (int)floorf(((float)y - 0.5f) / sy - 0.5f) - 1), yb = min(Ho - 1, (int)ceilf(((float)y + 1.5f) / sy - 0.5f) + 1);
+  const int xa = max(0, (int)floorf(((float)x - 0.5f) / sx - 0.5f) - 1), xb = min(Wo - 1, (int)ceilf(((float)x + 1.5f) / sx - 0.5f) + 1);
+  const float* g = dout + (long long)bc * Ho * Wo;
+  float acc = 0.f;
+  for (int oy = ya; oy <= yb; oy++) {
+    int y0, y1; float wy;
+    bil_src(oy, sy, Hi, y0, y1, wy);
+    const float cy = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
+    if (cy == 0.f) continue;
+    for (int ox = xa; ox <= xb; ox++) {
+      int x0, x1; float wx;
+      bil_src(ox, sx, Wi, x0, x1, wx);
+      const float cx = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
+      if (cx != 0.f) acc += cy * cx * g[(long long)oy * Wo + ox];
+    }
+  }
+  din[i] = acc;
+}
+
 }  // namespace gdu

@@ -261,9 +261,9 @@ class StableDiffusionGuidance:
         batch_size = rgb.shape[0]
         rgb_BCHW = rgb.permute(0, 3, 1, 2)
         if rgb_as_latents:
-            latents = F.interpolate(rgb_BCHW, (64, 64), mode="bilinear", align_corners=False)
+            latents = ops.resize_bilinear(rgb_BCHW, (64, 64))      # F.interpolate(..., "bilinear", align_corners=False)
         else:
-            latents = self.encode_images(F.interpolate(rgb_BCHW, (512, 512), mode="bilinear", align_corners=False))
+            latents = self.encode_images(ops.resize_bilinear(rgb_BCHW, (512, 512)))
         t = torch.randint(self.min_step, self.max_step + 1, [batch_size], dtype=torch.long, device=self.device,
                           generator=self.generator)
         grad, _ = self.compute_grad_sds(latents, t, prompt_utils, elevation, azimuth, camera_distances)

@@ -28,9 +28,10 @@ def _random_state_dict(seed, device):
 
 
 class SdsBenchStep:
-    def __init__(self, dev, views, state_dict=None, seed=0, use_cuda_graph=True, use_vae=True):
+    def __init__(self, dev, views, state_dict=None, seed=0, use_cuda_graph=True, use_vae=True, guidance_res=None):
         self.dev = torch.device(dev)
         self.B = views
+        self.guidance_res = guidance_res   # e.g. 512: renders of another size are resized (bilinear) before the VAE
         self.vae = None
         if use_vae:
             from .unet_init import random_vae_state_dict
@@ -59,9 +60,18 @@ class SdsBenchStep:
         """color [B,3,S,S] fp32 (rasteriser output) -> dL_sds/dcolor [B,3,S,S] fp32 of
         loss_sds = 0.5 * mse(latents, (latents - grad).detach(), 'sum') * scale (scale = 1/B by default:
         stable_diffusion_guidance.py:427; sharded views pass 1/(B*world))."""
-        B, _, H, W = color.shape
         L = ops.lib()
         stream = torch.cuda.current_stream().cuda_stream
+        full = None
+        if self.guidance_res and tuple(color.shape[-2:]) != (self.guidance_res, self.guidance_res):
+            # the reference renders at data.height x data.width (1024^2 shipped) and resizes to 512^2 for the guidance
+            # (stable_diffusion_guidance.py:387-396): bilinear forward here, its transpose on the way back
+            full = color
+            Bc, Cc, Hf, Wf = color.shape
+            color = torch.empty((Bc, Cc, self.guidance_res, self.guidance_res), dtype=torch.float32, device=full.device)
+            ops._chk(L.gd_resize_bilinear(full.data_ptr(), color.data_ptr(), Bc * Cc, Hf, Wf, self.guidance_res, self.guidance_res, stream),
+                     "resize_bilinear")
+        B, _, H, W = color.shape
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         if self.vae is not None:
@@ -87,6 +97,11 @@ class SdsBenchStep:
             dcol = torch.empty_like(color)
             ops._chk(L.gd_unet_pool_latents_bwd(grad.data_ptr(), self.mix.data_ptr(), dcol.data_ptr(), B, H, W, clip, scale,
                                                 stream), "pool_latents_bwd")
+        if full is not None:
+            dfull = torch.empty_like(full)
+            ops._chk(L.gd_resize_bilinear_bwd(dcol.data_ptr(), dfull.data_ptr(), B * 3, full.shape[2], full.shape[3], H, W, stream),
+                     "resize_bilinear_bwd")
+            dcol = dfull
         ev[3].record()
         self._vae_ms.append((ev[0], ev[1], ev[2], ev[3]))
         return dcol
@@ -164,5 +179,5 @@ def dominant_gemm_probe(dev, peaks):
     return out
 
 
-def make_bench_guidance(dev, views, use_vae=True):
-    return SdsBenchStep(dev, views, use_vae=use_vae)
+def make_bench_guidance(dev, views, use_vae=True, guidance_res=None):
+    return SdsBenchStep(dev, views, use_vae=use_vae, guidance_res=guidance_res)

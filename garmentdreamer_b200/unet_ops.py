@@ -96,6 +96,9 @@ def lib():
                      "pool_latents", "pool_latents_bwd"):
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
         L.gd_unet_init.restype = ctypes.c_int
+        L.gd_resize_bilinear.argtypes = [vp, vp, i, i, i, i, i, vp]
+        L.gd_resize_bilinear_bwd.argtypes = [vp, vp, i, i, i, i, i, vp]
+        L.gd_resize_bilinear.restype = L.gd_resize_bilinear_bwd.restype = ctypes.c_int
         _unet = L
     return _unet
 
@@ -500,3 +503,33 @@ def depth_to_space(x, out=None):
     out = torch.empty((N, 2 * Ho, 2 * Wo, C), dtype=torch.float16, device=x.device) if out is None else out
     _chk(lib().gd_unet_depth_to_space(_h(x).data_ptr(), out.data_ptr(), N, 2 * Ho, 2 * Wo, C, _stream()), "depth_to_space")
     return out
+
+
+class _ResizeBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        B, C, Hi, Wi = x.shape
+        ctx.shape = (B, C, Hi, Wi, Ho, Wo)
+        xin = x.detach().float().contiguous()
+        out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=x.device)
+        _chk(lib().gd_resize_bilinear(xin.data_ptr(), out.data_ptr(), B * C, Hi, Wi, Ho, Wo, _stream()), "resize_bilinear")
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, Hi, Wi, Ho, Wo = ctx.shape
+        gin = g.detach().float().contiguous()
+        out = torch.empty((B, C, Hi, Wi), dtype=torch.float32, device=g.device)
+        _chk(lib().gd_resize_bilinear_bwd(gin.data_ptr(), out.data_ptr(), B * C, Hi, Wi, Ho, Wo, _stream()), "resize_bilinear_bwd")
+        return out.to(g.dtype), None, None
+
+
+def resize_bilinear(x, size):
+    """F.interpolate(x, size, mode="bilinear", align_corners=False) for NCHW CUDA tensors (differentiable);
+    the identity when the size already matches."""
+    Ho, Wo = int(size[0]), int(size[1])
+    if tuple(x.shape[-2:]) == (Ho, Wo):
+        return x
+    if not x.is_cuda:
+        raise RuntimeError("resize_bilinear is CUDA-only (no CPU fallback)")
+    return _ResizeBilinear.apply(x, Ho, Wo)

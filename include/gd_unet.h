@@ -193,6 +193,12 @@ int gd_vae_sample_bwd(const float* grad, const void* moments, const float* noise
 int gd_vae_dimg(const void* dx, float* dcolor_nchw, int B, int H, int W, int Cp, float scale,
                 gd_ustream_t stream);
 
+/* F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=False) on fp32 planes [BC, Hi, Wi] -> [BC, Ho, Wo]
+   (stable_diffusion_guidance.py:387-396: the rendered batch is resized to 512^2 before encode_images), and its
+   transpose dout [BC, Ho, Wo] -> din [BC, Hi, Wi] (a deterministic gather). */
+int gd_resize_bilinear(const float* in, float* out, int BC, int Hi, int Wi, int Ho, int Wo, gd_ustream_t stream);
+int gd_resize_bilinear_bwd(const float* dout, float* din, int BC, int Hi, int Wi, int Ho, int Wo, gd_ustream_t stream);
+
 /* Bench glue, NOT part of the reference path: a fixed linear stand-in for the VAE encoder that
    the reference runs between the rasteriser and compute_grad_sds (encode_images, :160-167; out of
    this build's scope). latents [B,4,H/8,W/8] = mix[4][3] * mean_8x8(2*color-1); _bwd is its exact

@@ -145,3 +145,25 @@ def test_time_embedding_and_small_ops(ops):
     wo, bo = rnd(4, 3, 3, 320, scale=(9 * 320) ** -0.5), rnd(4)
     ref = F.conv2d(xo.float().permute(0, 3, 1, 2), wo.float().permute(0, 3, 1, 2), bo.float(), padding=1)
     assert rel(ops.conv_out(xo, wo, bo), ref) < 1e-3
+
+
+@pytest.mark.parametrize("hi,wi,ho,wo", [(1024, 1024, 512, 512), (96, 80, 64, 64), (48, 40, 64, 72), (64, 64, 64, 64)])
+def test_resize_bilinear_matches_interpolate_forward_and_backward(hi, wi, ho, wo):
+    """gd_resize_bilinear / _bwd == F.interpolate(mode="bilinear", align_corners=False) and its autograd
+    (stable_diffusion_guidance.py:387-396; 1024^2 -> 512^2 in the shipped config; up- and down-scaling, odd ratios)."""
+    import torch.nn.functional as F
+    from garmentdreamer_b200 import unet_ops as ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, hi, wi, generator=g).cuda()
+    dy = torch.randn(2, 3, ho, wo, generator=g).cuda()
+    xr = x.clone().requires_grad_(True)
+    ref = F.interpolate(xr, (ho, wo), mode="bilinear", align_corners=False)
+    ref.backward(dy)
+    xo = x.clone().requires_grad_(True)
+    y = ops.resize_bilinear(xo, (ho, wo))
+    if (hi, wi) == (ho, wo):
+        assert y is xo
+        return
+    y.backward(dy)
+    assert float((y - ref).abs().max()) < 1e-5
+    assert float((xo.grad - xr.grad).abs().max()) < 1e-4 * float(xr.grad.abs().max())
