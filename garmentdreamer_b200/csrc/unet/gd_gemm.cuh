@@ -52,6 +52,8 @@ struct GemmKParams {
   int tma_store;              // MODE 0: full 32-column chunks leave through shared memory + TMA store (tmC)
   int ksplit, kb_per_split;   // split-K: tile t covers k-blocks [ks*kb_per_split, ...) and writes fp32 partials
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
+  int a_halo;                 // CTA pairs, 3x3 conv on rows of >= 128 pixels: ONE haloed A tile (130 pixels x 64 ch) per (dy, channel
+                              // block) serves the three dx taps through row-shifted UMMA descriptors (A traffic / 3)
 };
 
 __device__ __forceinline__ uint32_t s2u(const void* p) {
@@ -105,6 +107,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// The same for a tile that starts `row_shift` 128-byte rows into a 1024-byte swizzle atom: the descriptor's base_offset
+// field (bits 49-51) = (start address >> 7) & 7 tells the unit where the XOR pattern of the atom begins.
+__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t atom_aligned_addr, uint32_t row_shift) {
+  return umma_desc_sw128(atom_aligned_addr + row_shift * 128u) | ((uint64_t)(row_shift & 7u) << 49);
+}
+constexpr uint32_t kHaloBytes = 17 * 1024;   // 130 rows x 128 B = 16640 B of haloed A, padded to the 1024-byte atom
 // Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, F16 x F16, K-major A and B.
 __device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -186,7 +194,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool bres = TWO && p.b_resident;
   if (bres && smem != smem_raw) __trap();   // resident mode is sized without the alignment slack (the base is 1 KB aligned)
   const uint32_t b_slot = (b_bytes + 1023) & ~1023u;
-  const uint32_t stage_bytes = bres ? a_bytes : a_bytes + b_slot;       // resident B: the ring holds A only
+  const bool halo = TWO && p.a_halo;
+  const uint32_t stage_bytes = halo ? kHaloBytes + 3 * b_slot : (bres ? a_bytes : a_bytes + b_slot);   // resident B: the ring holds A only
   uint8_t* b_res = smem + (size_t)S * stage_bytes;                      // [num_kb][b_slot] when resident
   uint8_t* stg_all = b_res + (bres ? (size_t)p.num_kb * b_slot : 0);    // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + (size_t)kEpiWarps * p.stg_bufs * 2048);
@@ -255,6 +264,23 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int b_c1 = n_blk * BN + (TWO ? (int)rank * (BN / 2) : 0) + zh * p.b_head_n;
         const int b_c2 = p.b_zdim > 1 ? zb : 0;
+        if (halo) {
+          // 3 x kb_per_tap super-blocks per tile: one 130-pixel row of A (x0-1 .. x0+128, image row y+dy; TMA zero-fills
+          // the pixels outside the image = the padding) and the three weight tiles of the taps (dy, dx = -1, 0, 1)
+          for (int dyi = 0; dyi < 3; dyi++)
+            for (int cb = 0; cb < p.kb_per_tap; cb++, it++) {
+              const int s = it % S;
+              bar_wait(&empty[s], ((it / S) & 1) ^ 1);
+              uint8_t* sa = smem + (size_t)s * stage_bytes;
+              uint8_t* sb = sa + kHaloBytes;
+              if (rank == 0) bar_expect_tx(&full[s], 2u * (130u * 128u + 3u * b_bytes));
+              tma_load_4d_2sm(sa, &tmA, &full[s], cb * kBK, a_c1 - 1, a_c2 + dyi - 1, a_c3);
+#pragma unroll
+              for (int dxi = 0; dxi < 3; dxi++)
+                tma_load_3d_2sm(sb + (size_t)dxi * b_slot, &tmB, &full[s], ((dyi * 3 + dxi) * p.kb_per_tap + cb) * kBK, b_c1, b_c2);
+            }
+          continue;
+        }
         for (int kb = kb0; kb < kb1; kb++, it++) {
           const int s = it % S;
           bar_wait(&empty[s], ((it / S) & 1) ^ 1);
@@ -295,6 +321,28 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_cols;
       const int ks = t % p.ksplit;
       const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      if (halo) {
+        const int nsb = 3 * p.kb_per_tap;
+        for (int sbk = 0; sbk < nsb; sbk++, it++) {
+          const int s = it % S;
+          bar_wait(&full[s], (it / S) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint32_t sa = s2u(smem + (size_t)s * stage_bytes), sb = sa + kHaloBytes;
+#pragma unroll
+            for (int dxi = 0; dxi < 3; dxi++) {
+              const uint64_t da = umma_desc_sw128_shifted(sa, (uint32_t)dxi), db = umma_desc_sw128(sb + (uint32_t)dxi * b_slot);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; k++)
+                umma_f16_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (sbk | dxi | k) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty[s]);
+            if (sbk == nsb - 1) umma_commit_2sm(&tmem_full[acc]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = kb0; kb < kb1; kb++, it++) {
         const int s = it % S;
         bar_wait(&full[s], (it / S) & 1);

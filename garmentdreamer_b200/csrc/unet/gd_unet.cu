@@ -722,11 +722,16 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   // CTA pairs (cta_group::2): every GEMM with at least two M tiles per batch entry
   static const bool pair_enabled = []() { const char* e = getenv("GD_GEMM_PAIR"); return !(e && e[0] == '0'); }();
   const bool two = pair_enabled && ksplit == 1 && m_tiles_all >= 2;
+  // haloed A tiles (one 130-pixel row per (dy, channel block) instead of three 128-pixel rows): 3x3 stride-1 convolutions over
+  // images at least 128 pixels wide, CTA pairs, plain epilogue. GD_GEMM_HALO=0 switches it off (A/B timing).
+  static const bool halo_enabled = []() { const char* e = getenv("GD_GEMM_HALO"); return !(e && e[0] == '0'); }();
+  bool a_halo = halo_enabled && two && a->ntaps == 9 && a->a_box[1] == gdu::kBM && a->a_box[2] == 1 && a->a_box[3] == 1 && a->Ck % gdu::kBK == 0;
+  for (int t = 0; a_halo && t < 9; t++) a_halo = a->tap_dx[t] == t % 3 - 1 && a->tap_dy[t] == t / 3 - 1 && a->tap_c[t] == 0;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->a_dim[0], (cuuint64_t)a->a_dim[1], (cuuint64_t)a->a_dim[2], (cuuint64_t)a->a_dim[3]};
     cuuint64_t str[3] = {(cuuint64_t)a->a_stride[0], (cuuint64_t)a->a_stride[1], (cuuint64_t)a->a_stride[2]};
-    cuuint32_t box[4] = {(cuuint32_t)a->a_box[0], (cuuint32_t)a->a_box[1], (cuuint32_t)a->a_box[2], (cuuint32_t)a->a_box[3]};
+    cuuint32_t box[4] = {(cuuint32_t)a->a_box[0], (cuuint32_t)(a->a_box[1] + (a_halo ? 2 : 0)), (cuuint32_t)a->a_box[2], (cuuint32_t)a->a_box[3]};
     const int rc = make_map(&tmA, a->A, 4, dims, str, box);
     if (rc != GD_UNET_OK) return rc;
   }
@@ -760,7 +765,9 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.row_bias_ld = a->row_bias_ld > 0 ? a->row_bias_ld : a->N;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
-  const size_t stage_bytes = (size_t)gdu::kBM * gdu::kBK * 2 + (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
+  const size_t b_slot_bytes = (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
+  const size_t stage_bytes = a_halo ? (size_t)gdu::kHaloBytes + 3 * b_slot_bytes : (size_t)gdu::kBM * gdu::kBK * 2 + b_slot_bytes;
+  p.a_halo = a_halo ? 1 : 0;
   // one persistent CTA per SM owns the shared memory: operand ring + epilogue staging + barriers/bias
   const int bias_stride = 32 * ((((BN + 31) / 32) + 1) / 2);   // bias floats per epilogue warp
   p.bias_stride = bias_stride;
@@ -782,7 +789,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   // (measured neutral on B200 -- 128->128 conv at 512^2: 367 us resident vs 378 us streamed -- so it is opt-in: GD_GEMM_BRES=1)
   static const bool bres_enabled = []() { const char* e = getenv("GD_GEMM_BRES"); return e && e[0] == '1'; }();
   p.b_resident = 0;
-  if (bres_enabled && two && n_tiles_all == 1 && a->batch == 1 && a->heads == 1) {
+  if (bres_enabled && !a_halo && two && n_tiles_all == 1 && a->batch == 1 && a->heads == 1) {
     const size_t a_bytes = (size_t)gdu::kBM * gdu::kBK * 2;
     const size_t b_slot = (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
     const size_t res = (size_t)num_kb_all * b_slot, stg = (size_t)gdu::kEpiWarps * stg_bufs * 2048;
