@@ -107,11 +107,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// The same for a tile that starts `row_shift` 128-byte rows into a 1024-byte swizzle atom: the descriptor's base_offset
-// field (bits 49-51) = (start address >> 7) & 7 tells the unit where the XOR pattern of the atom begins.
-__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t atom_aligned_addr, uint32_t row_shift) {
-  return umma_desc_sw128(atom_aligned_addr + row_shift * 128u) | ((uint64_t)(row_shift & 7u) << 49);
-}
 constexpr uint32_t kHaloBytes = 17 * 1024;   // 130 rows x 128 B = 16640 B of haloed A, padded to the 1024-byte atom
 // Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, F16 x F16, K-major A and B.
 __device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
@@ -195,7 +190,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (bres && smem != smem_raw) __trap();   // resident mode is sized without the alignment slack (the base is 1 KB aligned)
   const uint32_t b_slot = (b_bytes + 1023) & ~1023u;
   const bool halo = TWO && p.a_halo;
-  const uint32_t stage_bytes = halo ? kHaloBytes + 3 * b_slot : (bres ? a_bytes : a_bytes + b_slot);   // resident B: the ring holds A only
+  const uint32_t stage_bytes = halo ? (bres ? kHaloBytes : kHaloBytes + 3 * b_slot) : (bres ? a_bytes : a_bytes + b_slot);   // resident B: the ring holds A only
   uint8_t* b_res = smem + (size_t)S * stage_bytes;                      // [num_kb][b_slot] when resident
   uint8_t* stg_all = b_res + (bres ? (size_t)p.num_kb * b_slot : 0);    // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + (size_t)kEpiWarps * p.stg_bufs * 2048);
@@ -273,11 +268,13 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               bar_wait(&empty[s], ((it / S) & 1) ^ 1);
               uint8_t* sa = smem + (size_t)s * stage_bytes;
               uint8_t* sb = sa + kHaloBytes;
-              if (rank == 0) bar_expect_tx(&full[s], 2u * (130u * 128u + 3u * b_bytes));
+              if (rank == 0) bar_expect_tx(&full[s], 2u * (130u * 128u + (bres ? 0u : 3u * b_bytes)));
               tma_load_4d_2sm(sa, &tmA, &full[s], cb * kBK, a_c1 - 1, a_c2 + dyi - 1, a_c3);
+              if (!bres) {
 #pragma unroll
-              for (int dxi = 0; dxi < 3; dxi++)
-                tma_load_3d_2sm(sb + (size_t)dxi * b_slot, &tmB, &full[s], ((dyi * 3 + dxi) * p.kb_per_tap + cb) * kBK, b_c1, b_c2);
+                for (int dxi = 0; dxi < 3; dxi++)
+                  tma_load_3d_2sm(sb + (size_t)dxi * b_slot, &tmB, &full[s], ((dyi * 3 + dxi) * p.kb_per_tap + cb) * kBK, b_c1, b_c2);
+              }
             }
           continue;
         }
@@ -328,10 +325,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bar_wait(&full[s], (it / S) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            const uint32_t sa = s2u(smem + (size_t)s * stage_bytes), sb = sa + kHaloBytes;
+            const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
+            // weight tiles: behind the A tile in the stage, or (resident B) tap (dy, dx), channel block cb of the resident copy
+            const int dyi = sbk / p.kb_per_tap, cbi = sbk % p.kb_per_tap;
+            const uint32_t sb = bres ? s2u(b_res) + (uint32_t)((dyi * 3) * p.kb_per_tap + cbi) * b_slot : sa + kHaloBytes;
+            const uint32_t sb_step = bres ? (uint32_t)p.kb_per_tap * b_slot : b_slot;
 #pragma unroll
             for (int dxi = 0; dxi < 3; dxi++) {
-              const uint64_t da = umma_desc_sw128_shifted(sa, (uint32_t)dxi), db = umma_desc_sw128(sb + (uint32_t)dxi * b_slot);
+              // tap dx reads rows dx .. dx+127 of the 130-row tile: the descriptor simply starts dx rows (128 B each) later. The
+              // unit derives the 128B-swizzle XOR from the absolute shared-memory address bits [7:9], exactly like the TMA that
+              // wrote the tile, so no base_offset is set (measured: with base_offset = dx the result is wrong).
+              const uint64_t da = umma_desc_sw128(sa + (uint32_t)dxi * 128u), db = umma_desc_sw128(sb + (uint32_t)dxi * sb_step);
 #pragma unroll
               for (int k = 0; k < kBK / 16; k++)
                 umma_f16_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (sbk | dxi | k) ? 1u : 0u);

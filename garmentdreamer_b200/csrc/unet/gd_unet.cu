@@ -787,10 +787,13 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   // CTA pairs whose B tile is the same for every output tile (one N tile, no batch): keep this CTA's half of B
   // resident in shared memory for the whole kernel; the ring then streams A only
   // (measured neutral on B200 -- 128->128 conv at 512^2: 367 us resident vs 378 us streamed -- so it is opt-in: GD_GEMM_BRES=1)
-  static const bool bres_enabled = []() { const char* e = getenv("GD_GEMM_BRES"); return e && e[0] == '1'; }();
+  static const int bres_env = []() { const char* e = getenv("GD_GEMM_BRES"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+  // default: on together with the haloed A tiles (128->128 conv at 4x512^2: 375 us streamed, 282 us with the halo, 256 us with the
+  // halo and resident B), off otherwise (measured neutral there: those shapes are A-delivery bound)
+  const bool bres_enabled = bres_env >= 0 ? bres_env == 1 : a_halo;
   p.b_resident = 0;
-  if (bres_enabled && !a_halo && two && n_tiles_all == 1 && a->batch == 1 && a->heads == 1) {
-    const size_t a_bytes = (size_t)gdu::kBM * gdu::kBK * 2;
+  if (bres_enabled && two && n_tiles_all == 1 && a->batch == 1 && a->heads == 1) {
+    const size_t a_bytes = a_halo ? (size_t)gdu::kHaloBytes : (size_t)gdu::kBM * gdu::kBK * 2;
     const size_t b_slot = (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
     const size_t res = (size_t)num_kb_all * b_slot, stg = (size_t)gdu::kEpiWarps * stg_bufs * 2048;
     if (res + stg + fixed_noslack + 3 * a_bytes <= smem_max && (size_t)m_tiles_all * a->batch >= 4 * 148) {
@@ -818,7 +821,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   }
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
   const size_t smem = p.b_resident
-                          ? (size_t)stages * gdu::kBM * gdu::kBK * 2 + (size_t)num_kb_all * (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023) +
+                          ? (size_t)stages * (a_halo ? (size_t)gdu::kHaloBytes : (size_t)gdu::kBM * gdu::kBK * 2) + (size_t)num_kb_all * (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023) +
                                 (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed_noslack
                           : stages * stage_bytes + (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed;
   // output tensor map for the staged epilogue: [batch][head][M][N], 32 x 32 box, 64B swizzle
