@@ -52,6 +52,8 @@ struct GemmKParams {
   int tma_store;              // MODE 0: full 32-column chunks leave through shared memory + TMA store (tmC)
   int ksplit, kb_per_split;   // split-K: tile t covers k-blocks [ks*kb_per_split, ...) and writes fp32 partials
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
+  float* colstats;            // optional [ceil(M/32)][2][N]: per 32-row block and output column, sum and sum of squares of the fp16
+                              // values this GEMM stores (GroupNorm statistics of the consumer without another pass over the tensor)
   int a_halo;                 // CTA pairs, 3x3 conv on rows of >= 128 pixels: ONE haloed A tile (130 pixels x 64 ch) per (dy, channel
                               // block) serves the three dx taps through row-shifted UMMA descriptors (A traffic / 3)
 };
@@ -524,12 +526,48 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __syncwarp();
               const int piece = lane & 3;
               const int row0 = m_blk * kBM + q * 32;
+              float cs[8], cq[8];   // column sums / sums of squares over this lane's 4 rows (GroupNorm statistics)
+#pragma unroll
+              for (int u = 0; u < 8; u++) { cs[u] = 0.f; cq[u] = 0.f; }
 #pragma unroll
               for (int it = 0; it < 4; it++) {
                 const int r = it * 8 + (lane >> 2);
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
-                if (row0 + r < p.M)
+                if (row0 + r < p.M) {
                   *reinterpret_cast<uint4*>(p.C + coff + (long long)(row0 + r) * p.ldc + n0 + piece * 8) = val;
+                  if (p.colstats) {
+                    const __half2* hv = reinterpret_cast<const __half2*>(&val);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                      const float2 f = __half22float2(hv[u]);
+                      cs[2 * u] += f.x; cq[2 * u] += f.x * f.x; cs[2 * u + 1] += f.y; cq[2 * u + 1] += f.y * f.y;
+                    }
+                  }
+                }
+              }
+              if (p.colstats) {
+                // reduce-scatter over the 8 lanes that hold the same 8 columns (lane bits 2..4): 8 + 4 + 2 shuffles; afterwards a
+                // lane owns quantity b4 (sum | sum of squares) of columns piece*8 + b3*4 + b2*2 + {0, 1}. Fixed order: deterministic.
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                float a8[8], a4[4], a2[2];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                  const float send = b4 ? cs[u] : cq[u], keep = b4 ? cq[u] : cs[u];
+                  a8[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                  const float send = b3 ? a8[u] : a8[u + 4], keep = b3 ? a8[u + 4] : a8[u];
+                  a4[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                  const float send = b2 ? a4[u] : a4[u + 2], keep = b2 ? a4[u + 2] : a4[u];
+                  a2[u] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                const int col = n0 + piece * 8 + (b3 ? 4 : 0) + (b2 ? 2 : 0);
+                float* dstats = p.colstats + ((size_t)(row0 >> 5) * 2 + (b4 ? 1 : 0)) * p.N + col;
+                if (row0 < p.M) *reinterpret_cast<float2*>(dstats) = make_float2(a2[0], a2[1]);
               }
             } else if (p.tma_store == 1) {
               // registers -> swizzled staging tile -> one bulk tensor store per chunk (coalesced, async;

@@ -309,6 +309,66 @@ k_gn_cluster(const __half* __restrict__ x, __half* __restrict__ y, const __half*
   cluster_sync_all();   // peers may still be reading this CTA's partials
 }
 
+// ---- GroupNorm statistics from the column statistics of the producing GEMM(s) ---------------------------------------
+// colstats: [rowblocks][2][Cs] fp32 (sum | sum of squares per 32-row block and channel, written by k_gemm_tcgen05's epilogue):
+// 1/8 of the bytes of the fp16 tensor they describe. grid (image, splits): a CTA folds the row blocks of its slice of the
+// image with coalesced 16-byte loads (thread -> fixed column quad, row blocks strided over `lanes` thread groups), combines
+// the lanes and then the channels of a group in a fixed order (deterministic) and writes part[(n*groups+g)*splits + sp] --
+// the layout k_gn_stats produces, so the apply / finalize kernels are shared. The C channels are source A's Ca followed by
+// source B's Cb (torch.cat of the UNet up path).
+__device__ __forceinline__ void colstats_fold_source(const float* __restrict__ st, int Cs, int r0, int r1, float* s_lane,
+                                                     float* s_tot, int c_off, int C) {
+  const int Q = Cs >> 1;                                  // float4 per row block ([2][Cs] floats)
+  const int lanes = Q <= 256 ? 256 / Q : 1, iters = Q <= 256 ? 1 : (Q + 255) / 256;
+  for (int it = 0; it < iters; it++) {
+    const int q = Q <= 256 ? (int)(threadIdx.x % Q) : (int)threadIdx.x + 256 * it;
+    const int l = Q <= 256 ? (int)(threadIdx.x / Q) : 0;
+    if (l < lanes && q < Q) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = reinterpret_cast<const float4*>(st) + q;
+#pragma unroll 4
+      for (int rb = r0 + l; rb < r1; rb += lanes) {
+        const float4 v = src[(size_t)rb * Q];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (Q <= 256) reinterpret_cast<float4*>(s_lane)[l * Q + q] = acc;
+      else {   // one lane: straight into the totals ([sum | sumsq][C])
+        const int f = q * 4, half = f >= Cs ? 1 : 0, c = f - half * Cs;
+        float* d = s_tot + half * C + c_off + c;
+        d[0] = acc.x; d[1] = acc.y; d[2] = acc.z; d[3] = acc.w;
+      }
+    }
+  }
+  if (Q <= 256) {
+    __syncthreads();
+    for (int f = threadIdx.x; f < 2 * Cs; f += 256) {
+      float a = 0.f;
+      for (int l = 0; l < lanes; l++) a += s_lane[l * 2 * Cs + f];
+      const int half = f >= Cs ? 1 : 0;
+      s_tot[half * C + c_off + (f - half * Cs)] = a;
+    }
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256)
+k_gn_colstats_reduce(const float* __restrict__ statsA, int Ca, const float* __restrict__ statsB, int Cb, int rb_per_image,
+                     int groups, int splits, float2* __restrict__ part) {
+  pdl_entry();
+  __shared__ __align__(16) float s_lane[1024];   // lanes * 2 * Cs <= 1024 floats when Cs <= 512
+  __shared__ float s_tot[2 * 2560];              // [sum | sumsq][C]
+  const int n = blockIdx.x, sp = blockIdx.y, C = Ca + Cb, cpg = C / groups;
+  const int r0 = n * rb_per_image + (int)((long long)rb_per_image * sp / splits);
+  const int r1 = n * rb_per_image + (int)((long long)rb_per_image * (sp + 1) / splits);
+  colstats_fold_source(statsA, Ca, r0, r1, s_lane, s_tot, 0, C);
+  if (Cb > 0) colstats_fold_source(statsB, Cb, r0, r1, s_lane, s_tot, Ca, C);
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += s_tot[c]; b += s_tot[C + c]; }
+    part[((size_t)n * groups + g) * splits + sp] = make_float2(a, b);
+  }
+}
+
 // ---- LayerNorm: one warp per row -----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_layernorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
@@ -689,7 +749,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
       double best = -1.0;
       BN = 64;
       for (int c : cands) {
-        if (geglu && c % 32) continue;
+        if ((geglu || a->colstats) && c % 32) continue;   // whole 32-column epilogue chunks
         if (c > ((a->N + 15) / 16 * 16)) continue;
         if (a->N % c && !(c == 128 || c == 64)) continue;   // ragged N only with 128 / 64
         const long long tiles = mt * ((a->N + c - 1) / c);
@@ -838,6 +898,9 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     // 2 = staged + coalesced st.global (default); 1 = staged + TMA store (GD_GEMM_TMA_STORE=1)
     p.tma_store = use_tma_store ? 1 : 2;
   }
+  // fused GroupNorm column statistics need the staged store path and whole 32-column chunks
+  const bool colstats_ok = a->colstats && p.tma_store == 2 && a->N % 32 == 0 && BN % 32 == 0 && a->batch == 1;
+  p.colstats = colstats_ok ? reinterpret_cast<float*>(a->colstats) : nullptr;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -876,7 +939,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
         p.C, p.ldc, p.flags);
     LAUNCH_CHECK("k_splitk_finalize");
   }
-  return GD_UNET_OK;
+  return (a->colstats && !colstats_ok) ? GD_UNET_NO_COLSTATS : GD_UNET_OK;
 }
 
 int gd_unet_flash_attn(const void* q, const void* k, const void* vt, void* out, int B, int heads, int Tq, int Tk,
@@ -1078,6 +1141,30 @@ int gn_big_splits(int N, int HW, int C) {
 }
 }  // namespace
 
+// y = GN(x) (+SiLU) from the finalised (mean, rstd) table
+static int gn_apply_with_table(const void* x, void* y, const void* gamma, const void* beta, const float* stats, int N, int HW, int C,
+                               int groups, int silu, cudaStream_t s) {
+  const int C8 = C / 8;
+  if (256 % C8 == 0) {   // fast sweep: 4 loads in flight per thread
+    int pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 2);
+    const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+    if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
+    if (silu) launch_pdl(gdu::k_gn_apply_fast<true, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
+                         (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
+    else launch_pdl(gdu::k_gn_apply_fast<false, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
+                    (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
+    LAUNCH_CHECK("k_gn_apply_fast");
+    return GD_UNET_OK;
+  }
+  int pix_per_cta = (32768 + C - 1) / C;
+  const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+  if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
+  launch_pdl(gdu::k_gn_apply_final, dim3(N, (unsigned)chunks), dim3(256), (size_t)(sizeof(float2) * C), s, (const __half*)x,
+             (__half*)y, (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, pix_per_cta);
+  LAUNCH_CHECK("k_gn_apply_final");
+  return GD_UNET_OK;
+}
+
 int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const void* beta, float* stats, int N, int HW,
                             int C, int groups, float eps, int silu, gd_ustream_t s_) {
   cudaStream_t s = (cudaStream_t)s_;
@@ -1094,26 +1181,46 @@ int gd_unet_groupnorm_stats(const void* x, void* y, const void* gamma, const voi
   launch_pdl(gdu::k_gn_finalize, dim3((total + 7) / 8), dim3(256), (size_t)0, s, (const float2*)part, (float2*)stats, total,
              splits, 1.0f / ((float)HW * (float)(C / groups)), eps);
   LAUNCH_CHECK("k_gn_finalize");
-  if (y) {
-    const int C8 = C / 8;
-    if (256 % C8 == 0) {   // fast sweep: 4 loads in flight per thread
-      int pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 2);
-      const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
-      if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
-      if (silu) launch_pdl(gdu::k_gn_apply_fast<true, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
-                           (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
-      else launch_pdl(gdu::k_gn_apply_fast<false, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (__half*)y,
-                      (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, pix_per_cta);
-      LAUNCH_CHECK("k_gn_apply_fast");
-      return GD_UNET_OK;
-    }
-    int pix_per_cta = (32768 + C - 1) / C;
-    const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
-    if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_stats: image too large");
-    launch_pdl(gdu::k_gn_apply_final, dim3(N, (unsigned)chunks), dim3(256), (size_t)(sizeof(float2) * C), s, (const __half*)x,
-               (__half*)y, (const float2*)stats, (const __half*)gamma, (const __half*)beta, HW, C, groups, silu, pix_per_cta);
-    LAUNCH_CHECK("k_gn_apply_final");
+  if (y) return gn_apply_with_table(x, y, gamma, beta, stats, N, HW, C, groups, silu, s);
+  return GD_UNET_OK;
+}
+
+int gd_unet_groupnorm_colstats(const void* x, void* y, const void* gamma, const void* beta, float* mean_rstd, const float* statsA,
+                               int Ca, const float* statsB, int Cb, int N, int HW, int C, int groups, float eps, int silu,
+                               gd_ustream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (!x || !y || !statsA || Ca < 1 || Cb < 0 || (Cb > 0 && !statsB) || Ca + Cb != C)
+    return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_colstats: bad pointers / channel split");
+  if (C % groups || (C / groups) % 2 || C % 8 || Ca % 4 || Cb % 4 || groups > 256 || C > 2560 || HW % 32 || N * groups > 8192)
+    return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_colstats: C % 8 == 0, Ca % 4 == 0, Cb % 4 == 0, even channels per group, HW % 32 == 0");
+  DeviceScratch* sc = device_scratch();
+  if (!sc) return fail(GD_UNET_ERR_CUDA, "groupnorm_colstats: per-device scratch allocation failed");
+  float2* part = mean_rstd ? sc->gn_part : sc->gn_part_small;
+  const size_t cap = mean_rstd ? kGnBig : kGnSmall;
+  const int rbpi = HW / 32;
+  // ~2048 sixteen-byte loads per CTA, at least ~2 CTAs per SM when the image has the row blocks for it
+  long long splits = ((long long)rbpi * (C / 2) + 2047) / 2048;
+  if (splits > 512) splits = 512;
+  while (N * splits < 296 && splits * 2 <= rbpi && splits < 512) splits *= 2;
+  if (splits > rbpi) splits = rbpi;
+  if (splits < 1) splits = 1;
+  while ((size_t)N * groups * splits > cap && splits > 1) splits /= 2;
+  if ((size_t)N * groups * splits > cap) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_colstats: N * groups exceeds the scratch");
+  launch_pdl(gdu::k_gn_colstats_reduce, dim3(N, (unsigned)splits), dim3(256), (size_t)0, s, statsA, Ca, statsB, Cb, rbpi, groups,
+             (int)splits, part);
+  LAUNCH_CHECK("k_gn_colstats_reduce");
+  if (mean_rstd) {   // VAE flavour: (mean, rstd) table kept for the backward, fast sweeps
+    const int total = N * groups;
+    launch_pdl(gdu::k_gn_finalize, dim3((total + 7) / 8), dim3(256), (size_t)0, s, (const float2*)part, (float2*)mean_rstd, total,
+               (int)splits, 1.0f / ((float)HW * (float)(C / groups)), eps);
+    LAUNCH_CHECK("k_gn_finalize");
+    return gn_apply_with_table(x, y, gamma, beta, mean_rstd, N, HW, C, groups, silu, s);
   }
+  int pix_per_cta = (int)((16384 + C - 1) / C);
+  if (pix_per_cta < 1) pix_per_cta = 1;
+  launch_pdl(gdu::k_gn_apply, dim3(N, (HW + pix_per_cta - 1) / pix_per_cta), dim3(256), (size_t)(sizeof(float2) * C), s, (const __half*)x,
+             (__half*)y, (const float2*)part, (const __half*)gamma, (const __half*)beta, HW, C, groups, (int)splits, eps, silu, pix_per_cta);
+  LAUNCH_CHECK("k_gn_apply");
   return GD_UNET_OK;
 }
 

@@ -101,12 +101,12 @@ class UNetB200:
         off, c = self._temb_off[p]
         temb = emb[:, off:off + c]   # emb = all time_emb_proj outputs [B, sum(Cout)], row stride sum(Cout)
         h = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=1e-5, silu=True)
-        h = ops.conv3x3(h, w[p + ".conv1.weight"], w[p + ".conv1.bias"], row_bias=temb)
+        h = ops.conv3x3(h, w[p + ".conv1.weight"], w[p + ".conv1.bias"], row_bias=temb, want_stats=True)   # -> norm2
         h = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], eps=1e-5, silu=True, out=h)
         if p + ".conv_shortcut.weight" in w:
             x = ops.linear(x.view(N * H * W, Cin), w[p + ".conv_shortcut.weight"], w[p + ".conv_shortcut.bias"])
             x = x.view(N, H, W, -1)
-        out = ops.conv3x3(h, w[p + ".conv2.weight"], w[p + ".conv2.bias"], residual=x)
+        out = ops.conv3x3(h, w[p + ".conv2.weight"], w[p + ".conv2.bias"], residual=x, want_stats=True)   # -> the next block's norm
         if self._trace is not None:
             self._trace("resnet", p, x_in, out)
         return out
@@ -141,10 +141,11 @@ class UNetB200:
         n3 = ops.layernorm(h, w[b + ".norm3.weight"], w[b + ".norm3.bias"])
         f = ops.linear(n3, w[b + ".ff.net.0.proj.weight"], w[b + ".ff.net.0.proj.bias"], flags=ops.EPI_GEGLU)
         h = ops.linear(f, w[b + ".ff.net.2.weight"], w[b + ".ff.net.2.bias"], residual=h)
-        out = ops.linear(h, w[p + ".proj_out.weight"], w[p + ".proj_out.bias"], residual=x.view(N, H * W, C))
+        out = ops.linear(h, w[p + ".proj_out.weight"], w[p + ".proj_out.bias"], residual=x.view(N, H * W, C), want_stats=True)
+        out = ops.carry_stats(out, out.view(N, H, W, C))
         if self._trace is not None:
-            self._trace("transformer", p, x, out.view(N, H, W, C))
-        return out.view(N, H, W, C)
+            self._trace("transformer", p, x, out)
+        return out
 
     # ---- forward -------------------------------------------------------------------------------
     def _forward_impl(self, sample, t_f32, ctx):
@@ -168,7 +169,7 @@ class UNetB200:
                 skips.append(x)
             if i < 3:
                 p = f"down_blocks.{i}.downsamplers.0.conv"
-                x_in, x = x, ops.conv3x3_stride2(x, w[p + ".weight"], w[p + ".bias"])
+                x_in, x = x, ops.conv3x3_stride2(x, w[p + ".weight"], w[p + ".bias"], want_stats=True)
                 if self._trace is not None:
                     self._trace("down", p, x_in, x)
                 skips.append(x)
@@ -184,7 +185,7 @@ class UNetB200:
                     x = self._transformer(f"up_blocks.{i}.attentions.{j}", x, ctx, rev_heads[i])
             if i < 3:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
-                x_in, x = x, ops.conv3x3(ops.upsample2x(x), w[p + ".weight"], w[p + ".bias"])
+                x_in, x = x, ops.conv3x3(ops.upsample2x(x), w[p + ".weight"], w[p + ".bias"], want_stats=True)
                 if self._trace is not None:
                     self._trace("up", p, x_in, x)
         x_in = x

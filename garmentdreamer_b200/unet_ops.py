@@ -31,6 +31,7 @@ class GdGemmArgs(ctypes.Structure):
         ("bias", ctypes.c_void_p), ("row_bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("alpha", ctypes.c_float), ("flags", ctypes.c_uint), ("block_n", ctypes.c_int),
         ("row_bias_ld", ctypes.c_longlong),
+        ("colstats", ctypes.c_void_p),
     ]
 
 
@@ -96,6 +97,8 @@ def lib():
                      "pool_latents", "pool_latents_bwd"):
             getattr(L, "gd_unet_" + name).restype = ctypes.c_int
         L.gd_unet_init.restype = ctypes.c_int
+        L.gd_unet_groupnorm_colstats.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, f, i, vp]
+        L.gd_unet_groupnorm_colstats.restype = ctypes.c_int
         L.gd_resize_bilinear.argtypes = [vp, vp, i, i, i, i, i, vp]
         L.gd_resize_bilinear_bwd.argtypes = [vp, vp, i, i, i, i, i, vp]
         L.gd_resize_bilinear.restype = L.gd_resize_bilinear_bwd.restype = ctypes.c_int
@@ -109,6 +112,8 @@ _inited = set()
 def init_device(device=None):
     """Allocate the per-device scratch of libgd_unet.so for `device` (before any CUDA-graph capture)."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":   # host-side weight re-layout checks build the wrappers on the CPU; nothing to allocate
+        return
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     if idx in _inited:
         return
@@ -135,11 +140,41 @@ def _h(t):
     return t
 
 
-def _gemm(a: GdGemmArgs):
-    _chk(lib().gd_unet_gemm(ctypes.byref(a), _stream()), "gd_unet_gemm")
+def _gemm(a: GdGemmArgs, out=None, want_stats=False):
+    """Launches the GEMM. want_stats: ask the epilogue for the GroupNorm column statistics of the output
+    ([ceil(M/32), 2, N] fp32) and hang them on `out` (``out._gd_colstats = (stats, N)``) for the consuming
+    groupnorm(); silently absent when the kernel variant cannot produce them (split-K, ragged N)."""
+    stats = None
+    if want_stats and _FUSE_GN_STATS:
+        stats = torch.empty(((a.M + 31) // 32, 2, a.N), dtype=torch.float32, device=out.device)
+        a.colstats = stats.data_ptr()
+    rc = lib().gd_unet_gemm(ctypes.byref(a), _stream())
+    if rc not in (0, 1):
+        _chk(rc, "gd_unet_gemm")
+    if out is not None:
+        out._gd_colstats = (stats, a.N) if (stats is not None and rc == 0) else None
 
 
-def linear(x, w, bias=None, *, residual=None, out=None, flags=0, alpha=1.0, block_n=0):
+_FUSE_GN_STATS = os.environ.get("GD_FUSE_GN_STATS", "1") != "0"
+
+
+def carry_stats(src, dst):
+    """Views made of a GEMM output (reshape to NHWC, ...) keep its column statistics."""
+    dst._gd_colstats = getattr(src, "_gd_colstats", None)
+    return dst
+
+
+def _colstats_of(x):
+    """(statsA, Ca, statsB, Cb) if the tensor's producer(s) left column statistics, else None."""
+    cs = getattr(x, "_gd_colstats", None)
+    if cs is None:
+        return None
+    if len(cs) == 2:
+        return cs[0], cs[1], None, 0
+    return cs
+
+
+def linear(x, w, bias=None, *, residual=None, out=None, flags=0, alpha=1.0, block_n=0, want_stats=False):
     """y[M,N] = x[M,K] @ w[N,K]^T (+bias) (+residual); GEGLU flag halves N."""
     _h(x); _h(w)
     M, K = x.shape[-2] * (x.numel() // (x.shape[-1] * x.shape[-2])), x.shape[-1]
@@ -159,7 +194,7 @@ def linear(x, w, bias=None, *, residual=None, out=None, flags=0, alpha=1.0, bloc
     a.C, a.ldc = out.data_ptr(), (out.stride(-2) if out.dim() >= 2 else n_out)
     a.bias, a.residual = _p(bias), _p(residual)
     a.alpha, a.flags, a.block_n = alpha, flags, block_n
-    _gemm(a)
+    _gemm(a, out, want_stats)
     return out
 
 
@@ -203,7 +238,7 @@ def _conv_box(H, W, N):
     return W, H, rows // H
 
 
-def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0):
+def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False):
     """Implicit-GEMM convolution over NHWC x[N,H,W,Cx]: out[n,y,x,:] = sum_t x[n, y+dy_t, x+dx_t,
     c_t : c_t+Ck] @ w[:, t*Ck:(t+1)*Ck]^T (zero outside the image). taps = [(dx, dy, c)], w
     [Cout, len(taps)*Ck]. `out` may be a channel slice of a wider NHWC tensor."""
@@ -232,19 +267,20 @@ def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=No
     if row_bias is not None:
         a.row_bias_ld = row_bias.stride(0)
     a.alpha, a.flags = 1.0, flags
-    _gemm(a)
+    _gemm(a, out, want_stats)
     return out
 
 
 _TAPS_3X3 = [(t % 3 - 1, t // 3 - 1, 0) for t in range(9)]
 
 
-def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0):
+def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False):
     """3x3, stride 1, pad 1 over NHWC x[N,H,W,Cin]; w[Cout,3,3,Cin]."""
-    return conv_taps(x, w, _TAPS_3X3, x.shape[-1], bias, row_bias=row_bias, residual=residual, out=out, flags=flags)
+    return conv_taps(x, w, _TAPS_3X3, x.shape[-1], bias, row_bias=row_bias, residual=residual, out=out, flags=flags,
+                     want_stats=want_stats)
 
 
-def conv3x3_stride2(x, w, bias=None, *, s2d=None, out=None):
+def conv3x3_stride2(x, w, bias=None, *, s2d=None, out=None, want_stats=False):
     """3x3, stride 2, pad 1 (diffusers Downsample2D): space-to-depth, then 9 taps with shifts in
     {-1,0} over the 4 phase images (zero fill at the top/left border = the padding)."""
     _h(x); _h(w)
@@ -276,7 +312,7 @@ def conv3x3_stride2(x, w, bias=None, *, s2d=None, out=None):
     a.C, a.ldc = out.data_ptr(), Cout
     a.bias = _p(bias)
     a.alpha = 1.0
-    _gemm(a)
+    _gemm(a, out, want_stats)
     return out
 
 
@@ -373,7 +409,15 @@ def linear_transposed(x, w, Tk_pad, out=None, bias=None):
 def groupnorm(x, gamma, beta, groups=32, eps=1e-5, silu=False, out=None):
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
+    cs = _colstats_of(x)
     out = torch.empty_like(x) if out is None else out
+    out._gd_colstats = None
+    if cs is not None and HW % 32 == 0 and cs[1] + cs[3] == C:
+        # statistics came out of the producing GEMM epilogue(s): no statistics pass over x
+        _chk(lib().gd_unet_groupnorm_colstats(_h(x).data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), None,
+                                              cs[0].data_ptr(), cs[1], _p(cs[2]), cs[3], N, HW, C, groups, eps, int(silu), _stream()),
+             "groupnorm_colstats")
+        return out
     _chk(lib().gd_unet_groupnorm(_h(x).data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, HW, C, groups,
                                  eps, int(silu), _stream()), "groupnorm")
     return out
@@ -416,6 +460,8 @@ def upsample2x(x, out=None):
 def concat(a, b, out=None):
     Ca, Cb = a.shape[-1], b.shape[-1]
     out = torch.empty(a.shape[:-1] + (Ca + Cb,), dtype=torch.float16, device=a.device) if out is None else out
+    sa, sb = getattr(a, "_gd_colstats", None), getattr(b, "_gd_colstats", None)
+    out._gd_colstats = (sa[0], Ca, sb[0], Cb) if (sa is not None and sb is not None and len(sa) == 2 and len(sb) == 2) else None
     _chk(lib().gd_unet_concat(_h(a).data_ptr(), _h(b).data_ptr(), out.data_ptr(), a.numel() // Ca, Ca, Cb, _stream()), "concat")
     return out
 
@@ -461,6 +507,13 @@ def groupnorm_stats(x, gamma, beta, groups=32, eps=1e-6, silu=False, out=None, a
     stats = torch.empty((N * groups, 2), dtype=torch.float32, device=x.device)
     if apply and out is None:
         out = torch.empty_like(x)
+    cs = _colstats_of(x)
+    if apply and cs is not None and HW % 32 == 0 and cs[1] + cs[3] == C:
+        out._gd_colstats = None
+        _chk(lib().gd_unet_groupnorm_colstats(_h(x).data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                              cs[0].data_ptr(), cs[1], _p(cs[2]), cs[3], N, HW, C, groups, eps, int(silu), _stream()),
+             "groupnorm_colstats")
+        return out, stats
     _chk(lib().gd_unet_groupnorm_stats(_h(x).data_ptr(), out.data_ptr() if apply else None, gamma.data_ptr(), beta.data_ptr(),
                                        stats.data_ptr(), N, HW, C, groups, eps, int(silu), _stream()), "groupnorm_stats")
     return out, stats

@@ -101,13 +101,13 @@ class VAEEncoderB200:
     def _resnet_fwd(self, p, x, saved):
         w = self.w
         n1, st1 = ops.groupnorm_stats(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], eps=EPS, silu=True)
-        h1 = ops.conv3x3(n1, w[p + ".conv1.fwd"], w[p + ".conv1.bias"])
+        h1 = ops.conv3x3(n1, w[p + ".conv1.fwd"], w[p + ".conv1.bias"], want_stats=True)
         n2, st2 = ops.groupnorm_stats(h1, w[p + ".norm2.weight"], w[p + ".norm2.bias"], eps=EPS, silu=True, out=n1 if n1.shape == h1.shape else None)
         sc = x
         if p + ".conv_shortcut.fwd" in w:
             N, H, W, C = x.shape
             sc = ops.linear(x.view(N * H * W, C), w[p + ".conv_shortcut.fwd"], w[p + ".conv_shortcut.bias"]).view(N, H, W, -1)
-        out = ops.conv3x3(n2, w[p + ".conv2.fwd"], w[p + ".conv2.bias"], residual=sc)
+        out = ops.conv3x3(n2, w[p + ".conv2.fwd"], w[p + ".conv2.bias"], residual=sc, want_stats=True)
         saved.append(("resnet", p, x, st1, h1, st2))
         if self._trace is not None:
             self._trace("resnet", p, x, out)
@@ -134,7 +134,7 @@ class VAEEncoderB200:
         C = x.shape[-1]
         taps = [(dx, dy, ph * C) for dx, dy, ph in _DOWN_TAPS]
         saved.append(("down", p, C))
-        out = ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"])
+        out = ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"], want_stats=True)
         if self._trace is not None:
             self._trace("down", p, x, out)
         return out
@@ -163,7 +163,8 @@ class VAEEncoderB200:
         scale = float(C) ** -0.5
         P = ops.softmax_(ops.bmm_nt(q, k, alpha=scale), T)     # [N,T,T]; one head of 512
         o = ops.bmm_nt(P, ops.transpose(v))                    # P @ v
-        out = ops.linear(o, w[p + ".to_out.0.fwd"], w[p + ".to_out.0.bias"], residual=x.view(N, T, C)).view(N, H, W, C)
+        out = ops.linear(o, w[p + ".to_out.0.fwd"], w[p + ".to_out.0.bias"], residual=x.view(N, T, C), want_stats=True)
+        out = ops.carry_stats(out, out.view(N, H, W, C))
         saved.append(("attn", p, x, st, q, k, v, P, scale))
         if self._trace is not None:
             self._trace("attn", p, x, out)
@@ -206,7 +207,8 @@ class VAEEncoderB200:
         cols = torch.empty((B * H * W, 64), dtype=torch.float16, device=imgs.device)
         ops._chk(L.gd_vae_im2col(imgs.data_ptr(), cols.data_ptr(), B, H, W, a, sh, st), "vae_im2col")
         saved = []
-        x = ops.linear(cols, self.w["conv_in.fwd"], self.w["encoder.conv_in.bias"]).view(B, H, W, -1)
+        x = ops.linear(cols, self.w["conv_in.fwd"], self.w["encoder.conv_in.bias"], want_stats=True)
+        x = ops.carry_stats(x, x.view(B, H, W, -1))
         for i in range(4):
             for j in range(2):
                 x = self._resnet_fwd(f"encoder.down_blocks.{i}.resnets.{j}", x, saved)

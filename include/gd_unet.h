@@ -23,6 +23,7 @@ extern "C" {
 #endif
 
 #define GD_UNET_OK 0
+#define GD_UNET_NO_COLSTATS 1
 #define GD_UNET_ERR_INVALID_ARG (-1)
 #define GD_UNET_ERR_CUDA (-3)
 
@@ -71,6 +72,11 @@ typedef struct {
   unsigned flags;
   int block_n;            /* 16..256, multiple of 16; 0 = choose */
   long long row_bias_ld;  /* row stride of row_bias in elements; 0 = N */
+  /* optional fused GroupNorm statistics of the OUTPUT (plain epilogue only): fp32 [ceil(M/32)][2][N], per 32-row block
+     and column the sum and the sum of squares of the fp16 values stored. gd_unet_gemm returns GD_UNET_NO_COLSTATS (1) when
+     the chosen kernel variant cannot produce them (split-K, ragged N, transposed / GEGLU epilogue): the output tensor is
+     complete, the statistics are not written. */
+  void* colstats;
 } GdGemmArgs;
 
 int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
@@ -192,6 +198,14 @@ int gd_vae_sample_bwd(const float* grad, const void* moments, const float* noise
 /* d image: fp16 NHWC [B,H,W,Cp] (3 real channels) -> fp32 NCHW [B,3,H,W] * scale. */
 int gd_vae_dimg(const void* dx, float* dcolor_nchw, int B, int H, int W, int Cp, float scale,
                 gd_ustream_t stream);
+
+/* GroupNorm (+SiLU) of x fp16 NHWC [N,HW,C] from the column statistics a producing gd_unet_gemm left behind (GdGemmArgs.colstats)
+   instead of a statistics pass over x. The C channels are the concatenation of Ca channels described by statsA and Cb by statsB
+   (torch.cat([x, skip], 1) of the UNet up path; Cb = 0 / statsB = NULL for a single producer); both cover the same N*HW rows,
+   HW % 32 == 0. Writes y; if mean_rstd != NULL also the fp32 (mean, rstd) table [N*groups][2] the backward needs. */
+int gd_unet_groupnorm_colstats(const void* x, void* y, const void* gamma, const void* beta, float* mean_rstd,
+                               const float* statsA, int Ca, const float* statsB, int Cb, int N, int HW, int C,
+                               int groups, float eps, int silu, gd_ustream_t stream);
 
 /* F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=False) on fp32 planes [BC, Hi, Wi] -> [BC, Ho, Wo]
    (stable_diffusion_guidance.py:387-396: the rendered batch is resized to 512^2 before encode_images), and its

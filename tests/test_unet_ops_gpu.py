@@ -126,6 +126,39 @@ def test_norms_and_elementwise(ops):
     assert torch.equal(ops.concat(p, q), torch.cat([p, q], -1))
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 32, 32, 320, 640), (8, 16, 16, 1280, 1280), (1, 64, 64, 320, 320), (2, 128, 128, 128, 128)])
+def test_gemm_colstats_feed_groupnorm(ops, N, H, W, Cin, Cout):
+    """GroupNorm statistics emitted by the producing GEMM epilogue (GdGemmArgs.colstats): the per-32-row column sums match
+    the stored fp16 output, and groupnorm() consuming them equals groupnorm() with its own statistics pass."""
+    x, w, b = rnd(N, H, W, Cin), rnd(Cout, 3, 3, Cin, scale=(9 * Cin) ** -0.5), rnd(Cout)
+    y = ops.conv3x3(x, w, b, want_stats=True)
+    cs = getattr(y, "_gd_colstats", None)
+    assert cs is not None and cs[0] is not None, "the plain conv epilogue must produce column statistics"
+    st = cs[0]
+    yf = y.float().view(-1, 32, Cout)
+    assert st.shape == (yf.shape[0], 2, Cout)
+    assert (st[:, 0] - yf.sum(1)).abs().max() < 1e-3 * max(1.0, float(yf.sum(1).abs().max()))
+    assert (st[:, 1] - (yf * yf).sum(1)).abs().max() < 1e-3 * float((yf * yf).sum(1).abs().max())
+    g, be = rnd(Cout), rnd(Cout)
+    fused = ops.groupnorm(y, g, be, eps=1e-5, silu=True)
+    y2 = y.clone()
+    plain = ops.groupnorm(y2, g, be, eps=1e-5, silu=True)
+    ref = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, g.float(), be.float(), 1e-5)).permute(0, 2, 3, 1)
+    assert rel(fused, ref) < 1e-3 and rel(fused, plain) < 2e-4
+    # concatenated sources (UNet up path): both producers' statistics are used
+    y3 = ops.conv3x3(x, w, b, want_stats=True)
+    cat = ops.concat(y, y3)
+    assert getattr(cat, "_gd_colstats", None) is not None
+    g2, b2 = rnd(2 * Cout), rnd(2 * Cout)
+    fused = ops.groupnorm(cat, g2, b2, eps=1e-5, silu=True)
+    ref = F.silu(F.group_norm(cat.float().permute(0, 3, 1, 2), 32, g2.float(), b2.float(), 1e-5)).permute(0, 2, 3, 1)
+    assert rel(fused, ref) < 1e-3
+    # VAE flavour: (mean, rstd) table for the backward
+    out, stats = ops.groupnorm_stats(y, g, be, eps=1e-6, silu=True)
+    out2, stats2 = ops.groupnorm_stats(y.clone(), g, be, eps=1e-6, silu=True)
+    assert rel(out, out2) < 2e-4 and rel(stats, stats2) < 1e-4
+
+
 def test_time_embedding_and_small_ops(ops):
     t = torch.tensor([20.0, 500.0, 979.0, 980.0], device="cuda")
     e = ops.timestep_embedding(t, 320)
