@@ -978,9 +978,19 @@ int gd_unet_flash_attn_ex(const void* q, const void* k, const void* vt, void* ou
   const size_t smem = gdu::kQBytes + 2 * gdu::kKBytes + 2 * gdu::kVBytes + 2 * gdu::kPBytes + 1024 + 256 + 1024 + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gdu::k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(gdu::k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_flash_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail(GD_UNET_ERR_CUDA, "flash_attn: cannot raise dynamic shared memory limit");
     attr_set = true;
+  }
+  // long key ranges (self-attention of the 64^2 / 32^2 / 16^2 latent layers): single-pass kernel, two Q tiles per CTA.
+  // GD_ATTN_TWO_PASS=1 keeps the two-pass kernel for A/B timing.
+  static const bool two_pass_only = []() { const char* e = getenv("GD_ATTN_TWO_PASS"); return e && e[0] == '1'; }();
+  if (!two_pass_only && p.n_kv >= 2) {
+    const size_t smem2 = 2 * gdu::kQBytes + gdu::kAttn2Stages * (gdu::kKBytes + gdu::kVBytes) + 1024 + 512;
+    launch_pdl(gdu::k_flash_attn2, dim3((Tq + 255) / 256, B * heads), dim3(gdu::kAttn2Threads), smem2, stream, tmQ, tmK, tmV, p);
+    LAUNCH_CHECK("k_flash_attn2");
+    return GD_UNET_OK;
   }
   launch_pdl(gdu::k_flash_attn, dim3(dim3((Tq + 127) / 128, B * heads)), dim3(gdu::kAttnThreads), (size_t)(smem), (cudaStream_t)(stream), tmQ, tmK, tmV, p);
   LAUNCH_CHECK("k_flash_attn");

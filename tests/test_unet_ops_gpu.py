@@ -105,6 +105,26 @@ def test_attention(ops, B, Tq, Tk, heads):
     assert rel(of, o_ref) < 3e-3 and maxrel(of, o_ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,Tq,Tk,heads,gain", [(1, 384, 300, 5, 1.0), (2, 1024, 1024, 10, 3.0), (1, 4096, 4096, 5, 4.0), (1, 200, 640, 2, 2.0)])
+def test_attention_single_pass_lazy_rescale(ops, B, Tq, Tk, heads, gain):
+    """k_flash_attn2 (key ranges of >= 2 tiles): ragged Tq / Tk, and logits whose row maxima keep growing along the key
+    axis (keys sorted by norm, large gain) so the lazy running maximum moves and O is rescaled in TMEM several times."""
+    C = heads * 64
+    q, k, v = rnd(B, Tq, C, scale=gain), rnd(B, Tk, C, seed=1), rnd(B, Tk, C, seed=2)
+    ramp = torch.linspace(0.2, gain, Tk, device="cuda").view(1, Tk, 1)
+    k = (k.float() * ramp).half()
+    ldv = (Tk + 7) // 8 * 8
+    vt = torch.zeros(B, C, ldv, dtype=torch.float16, device="cuda")
+    vt[:, :, :Tk] = v.transpose(1, 2)
+    qh = q.float().view(B, Tq, heads, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Tk, heads, 64).permute(0, 2, 1, 3)
+    vh = v.float().view(B, Tk, heads, 64).permute(0, 2, 1, 3)
+    o_ref = ((0.125 * qh @ kh.transpose(-1, -2)).softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B, Tq, C)
+    o = ops.flash_attention(q, k, vt, heads, Tk, 0.125)
+    assert torch.isfinite(o).all()
+    assert rel(o, o_ref) < 3e-3 and maxrel(o, o_ref) < 1e-2
+
+
 def test_norms_and_elementwise(ops):
     x = rnd(2, 32, 32, 640)
     g, b = rnd(640), rnd(640)
