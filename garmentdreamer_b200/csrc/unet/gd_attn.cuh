@@ -21,6 +21,7 @@ struct AttnParams {
   float scale_log2e;     // softmax scale * log2(e)
   __half* O;             // [B, Tq, ldo]
   long long ldo;
+  int stagger;           // k_flash_attn2: cycles the second softmax warpgroup starts late (keeps the two out of lockstep)
 };
 
 constexpr int kAttnThreads = 64 + 8 * 32;  // producer, issuer, 8 softmax warps (2 per TMEM lane quarter)
@@ -440,6 +441,12 @@ k_flash_attn2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < n; j++) {
         bar_wait(&s_full[q], j & 1);
+        if (j == 0 && q == 1 && p.stagger > 0) {
+          // Both warpgroups would otherwise run in lockstep (S0 and S1 land back to back): their ex2 phases then collide on the
+          // SFU and their LDTM / max / STTM phases leave it idle together. Half a period of offset makes one fill the other's gap.
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger) {}
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[128];
         tmem_ld32_issue(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -456,13 +463,15 @@ k_flash_attn2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           for (int t = 0; t < 128; t++)
             if (t >= kvalid) v[t] = 0xff800000u;   // -inf
         }
-        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+        float mm[8];                               // 8 independent FMNMX3 chains
 #pragma unroll
-        for (int t = 4; t < 128; t += 4) {
-          m0 = fmaxf(m0, __uint_as_float(v[t])); m1 = fmaxf(m1, __uint_as_float(v[t + 1]));
-          m2 = fmaxf(m2, __uint_as_float(v[t + 2])); m3 = fmaxf(m3, __uint_as_float(v[t + 3]));
+        for (int u = 0; u < 8; u++) mm[u] = fmaxf(__uint_as_float(v[u]), __uint_as_float(v[u + 8]));
+#pragma unroll
+        for (int t = 16; t < 128; t += 16) {
+#pragma unroll
+          for (int u = 0; u < 8; u++) mm[u] = fmaxf(mm[u], fmaxf(__uint_as_float(v[t + u]), __uint_as_float(v[t + u + 8])));
         }
-        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float mx = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), fmaxf(fmaxf(mm[4], mm[5]), fmaxf(mm[6], mm[7])));
         const bool grow = (mx - m) * c > 8.0f;     // lazy: the reference maximum moves only on a 2^8 overshoot (always at j = 0)
         float factor = 1.0f;
         if (grow) { factor = ex2_approx((m - mx) * c); m = mx; }

@@ -975,6 +975,8 @@ int gd_unet_flash_attn_ex(const void* q, const void* k, const void* vt, void* ou
   p.Tq = Tq; p.Tk = Tk; p.heads = heads; p.n_kv = (Tk + 127) / 128;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.O = reinterpret_cast<__half*>(out); p.ldo = ldo;
+  static const int stagger = []() { const char* e = getenv("GD_ATTN_STAGGER"); return e ? atoi(e) : 800; }();
+  p.stagger = stagger;
   const size_t smem = gdu::kQBytes + 2 * gdu::kKBytes + 2 * gdu::kVBytes + 2 * gdu::kPBytes + 1024 + 256 + 1024 + 64;
   static bool attr_set = false;
   if (!attr_set) {
