@@ -1246,8 +1246,15 @@ int gd_unet_groupnorm_bwd(const void* x, const void* dz, const void* add, void* 
   float2* bstats = device_scratch()->gn_bstats;
   const int splits = gn_big_splits(N, HW, C);
   if ((size_t)N * groups * splits > kGnBig) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: N * groups * splits exceeds the scratch");
-  launch_pdl(gdu::k_gn_bwd_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
-             (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits, silu);
+  if (256 % (C / 8) == 0) {   // register-resident coefficients, software-pipelined loads
+    if (silu) launch_pdl(gdu::k_gn_bwd_stats_fast<true, 2>, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
+                         (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits);
+    else launch_pdl(gdu::k_gn_bwd_stats_fast<false, 2>, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
+                    (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits);
+  } else {
+    launch_pdl(gdu::k_gn_bwd_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
+               (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits, silu);
+  }
   LAUNCH_CHECK("k_gn_bwd_stats");
   const int total = N * groups;
   launch_pdl(gdu::k_gn_bwd_finalize, dim3((total + 7) / 8), dim3(256), (size_t)0, s, (const float2*)part, bstats, total, splits,

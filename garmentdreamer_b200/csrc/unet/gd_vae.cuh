@@ -71,8 +71,12 @@ k_gn_apply_final(const __half* __restrict__ x, __half* __restrict__ y, const flo
 // g = dz * act'(y):   dx = rstd * (gamma*g - S1 - xh*S2),  S1 = mean_group(gamma*g),
 // S2 = mean_group(gamma*g*xh).
 __device__ __forceinline__ float dsilu(float y) {
-  const float s = __fdividef(1.0f, 1.0f + __expf(-y));
-  return s * (1.0f + y * (1.0f - s));
+  // sigmoid(y) = 0.5 + 0.5 tanh(y/2): ONE SFU op (tanh.approx, |rel err| <= 2^-11 -- below the fp16 rounding of the
+  // result) instead of ex2 + rcp; the GroupNorm backward sweeps were SFU/issue-bound on the two-op form.
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  const float s = fmaf(0.5f, t, 0.5f);
+  return s * fmaf(y, 1.0f - s, 1.0f);
 }
 // Pass 1: same sweep as k_gn_stats; per channel sum(g), sum(g*xh) folded with gamma per group.
 __global__ void __launch_bounds__(256)
@@ -128,6 +132,76 @@ k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dz, cons
     float u = 0.f, v = 0.f;
     for (int pl = 0; pl < pix_par; pl++)
       for (int c = g * cpg; c < (g + 1) * cpg; c++) { u += s_c[0][pl * C + c]; v += s_c[1][pl * C + c]; }
+    part[((size_t)n * groups + g) * splits + sp] = make_float2(u, v);
+  }
+}
+// Pass 1, fast flavour (C/8 divides 256: the VAE's 128 / 256 / 512 channels): a thread owns ONE 8-channel chunk for the
+// whole sweep -- coefficients in registers (xh = x*ca + cb, y = x*ya + yb), no index arithmetic -- with the 16-byte loads of
+// the next U pixels in flight during the math. Same partial layout as k_gn_bwd_stats.
+template <bool SILU, int U>
+__global__ void __launch_bounds__(256)
+k_gn_bwd_stats_fast(const __half* __restrict__ x, const __half* __restrict__ dz, const float2* __restrict__ stats,
+                    const __half* __restrict__ gamma, const __half* __restrict__ beta, float2* __restrict__ part,
+                    int HW, int C, int groups, int splits) {
+  pdl_entry();
+  __shared__ float s_c[2][2048];   // [sum g*gamma | sum g*gamma*xh][pl * C + c]   (PP * C = 2048)
+  const int n = blockIdx.x, sp = blockIdx.y;
+  const int cpg = C / groups, C8 = C >> 3, PP = 256 / C8;
+  const int ch = threadIdx.x % C8, pl = threadIdx.x / C8;
+  const int p0 = (int)((long long)HW * sp / splits), p1 = (int)((long long)HW * (sp + 1) / splits);
+  float ca[8], cb[8], ya[8], yb[8], gam[8], sg[8], sx[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = ch * 8 + k;
+    const float2 mr = stats[(size_t)n * groups + c / cpg];
+    gam[k] = __half2float(gamma[c]);
+    ca[k] = mr.y; cb[k] = -mr.x * mr.y;
+    ya[k] = ca[k] * gam[k]; yb[k] = fmaf(cb[k], gam[k], __half2float(beta[c]));
+    sg[k] = 0.f; sx[k] = 0.f;
+  }
+  const size_t base = (size_t)n * HW * C;
+  const uint4* xb = reinterpret_cast<const uint4*>(x + base) + ch;
+  const uint4* gb = reinterpret_cast<const uint4*>(dz + base) + ch;
+  uint4 xv[U], gv[U], nxv[U], ngv[U];
+  auto fetch = [&](int pp, uint4 (&X)[U], uint4 (&G)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const bool ok = pp + u * PP < p1;
+      const size_t o = (size_t)(pp + u * PP) * C8;
+      X[u] = ok ? xb[o] : make_uint4(0, 0, 0, 0);
+      G[u] = ok ? gb[o] : make_uint4(0, 0, 0, 0);   // zero gradient: padding pixels add nothing
+    }
+  };
+  fetch(p0 + pl, nxv, ngv);
+  for (int pix = p0 + pl; pix < p1; pix += PP * U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) { xv[u] = nxv[u]; gv[u] = ngv[u]; }
+    fetch(pix + PP * U, nxv, ngv);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const __half2* xh2 = reinterpret_cast<const __half2*>(&xv[u]);
+      const __half2* gh2 = reinterpret_cast<const __half2*>(&gv[u]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 xf = __half22float2(xh2[k]), gf = __half22float2(gh2[k]);
+        float g0 = gf.x, g1 = gf.y;
+        if (SILU) { g0 *= dsilu(fmaf(xf.x, ya[2 * k], yb[2 * k])); g1 *= dsilu(fmaf(xf.y, ya[2 * k + 1], yb[2 * k + 1])); }
+        sg[2 * k] += g0; sx[2 * k] = fmaf(g0, fmaf(xf.x, ca[2 * k], cb[2 * k]), sx[2 * k]);
+        sg[2 * k + 1] += g1; sx[2 * k + 1] = fmaf(g1, fmaf(xf.y, ca[2 * k + 1], cb[2 * k + 1]), sx[2 * k + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    s_c[0][pl * C + ch * 8 + k] = sg[k] * gam[k];
+    s_c[1][pl * C + ch * 8 + k] = sx[k] * gam[k];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float u = 0.f, v = 0.f;
+    for (int q = 0; q < PP; q++)
+      for (int c = g * cpg; c < (g + 1) * cpg; c++) { u += s_c[0][q * C + c]; v += s_c[1][q * C + c]; }
     part[((size_t)n * groups + g) * splits + sp] = make_float2(u, v);
   }
 }
