@@ -48,12 +48,9 @@ __device__ __forceinline__ float adam_step(float p, float g, float& m, float& v,
 // grad: packed gradient w.r.t. the ACTIVATED parameters (rasteriser backward output, same layout
 // as k_params_activate's output); the chain rule through the activations and the Adam update of
 // the RAW parameters happen here. exp_avg / exp_avg_sq: packed [14P] optimiser state.
-__global__ void __launch_bounds__(256)
-k_params_adam(int P, float* __restrict__ xyz, float* __restrict__ f_dc, float* __restrict__ opacity,
-              float* __restrict__ scaling, float* __restrict__ rotation, const float* __restrict__ grad,
-              float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, AdamHyper h) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
+__device__ __forceinline__ void adam_one(int i, int P, float* __restrict__ xyz, float* __restrict__ f_dc, float* __restrict__ opacity,
+                                         float* __restrict__ scaling, float* __restrict__ rotation, const float* __restrict__ grad,
+                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, const AdamHyper& h) {
   const size_t o_dc = 3 * (size_t)P, o_op = 6 * (size_t)P, o_sc = 7 * (size_t)P, o_rot = 10 * (size_t)P;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -85,6 +82,14 @@ k_params_adam(int P, float* __restrict__ xyz, float* __restrict__ f_dc, float* _
     }
     *reinterpret_cast<float4*>(rotation + 4 * (size_t)i) = make_float4(r[0], r[1], r[2], r[3]);
   }
+}
+__global__ void __launch_bounds__(256)
+k_params_adam(int P, float* __restrict__ xyz, float* __restrict__ f_dc, float* __restrict__ opacity,
+              float* __restrict__ scaling, float* __restrict__ rotation, const float* __restrict__ grad,
+              float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, AdamHyper h) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  adam_one(i, P, xyz, f_dc, opacity, scaling, rotation, grad, exp_avg, exp_avg_sq, h);
 }
 
 // gaussian_model.py:415-419 + GaussianDreamer.py:269-275 for the view batch: visibility = max
@@ -225,6 +230,122 @@ __global__ void k_cameras_from_c2w(int B, const float* __restrict__ c2w, CamIntr
   o[32] = -(c00 * tx + c01 * ty + c02 * tz) * inv_det;
   o[33] = -(c10 * tx + c11 * ty + c12 * tz) * inv_det;
   o[34] = -(c20 * tx + c21 * ty + c22 * tz) * inv_det;
+}
+
+
+// ---- multi-GPU: the gradient exchange over peer memory, fused with the optimiser step (SURVEY.md s.8 row e) --------
+// Views are sharded over ranks; the per-Gaussian gradients [17P] (14P parameters | 3P viewspace) and the radii maxima [P]
+// of every rank live in a symmetric allocation mapped into every peer (NVLink / NVSwitch). Instead of
+// NCCL all-reduce(grad) + all-reduce(radii) + k_densify_stats + k_params_adam (four launches, two stream hops):
+//   k_peer_allreduce      rank r sums slice r of the W gradient buffers straight out of the peers' memory (P2P loads in a
+//                         fixed rank order, or ONE multimem.ld_reduce per 16 bytes when the allocation has an NVLS multicast
+//                         address: the switch adds) and pushes the result into every rank's reduced buffer (P2P stores /
+//                         multimem.st). Its entry barrier (flags[0]) is the one cross-rank synchronisation of the step.
+//   k_params_adam_peers   waits (flags[1]) until every slice has landed, then densification statistics + Adam on the
+//                         local replica. Every rank adds in the same order: replicas stay bit-identical.
+// Flags are monotonically increasing epochs written with st.release.sys into the PEER's flag array and polled locally.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_signal(const GdPeerTable& t, int phase, unsigned epoch) {   // threads 0..world-1
+  if ((int)threadIdx.x < t.world) {
+    __threadfence_system();
+    st_release_sys(t.flags[threadIdx.x] + phase * GD_MAX_PEERS + t.rank, epoch);
+  }
+}
+__device__ __forceinline__ void peer_wait(const GdPeerTable& t, int phase, unsigned epoch) {
+  if ((int)threadIdx.x < t.world) {
+    const unsigned* f = t.flags[t.rank] + phase * GD_MAX_PEERS + threadIdx.x;
+    while ((int)(ld_acquire_sys(f) - epoch) < 0) {}
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {   // peer memory: bypass L1, nothing to reuse
+  float4 v;
+  asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int4 ld_peer4i(const int* p) {
+  int4 v;
+  asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256)
+k_peer_allreduce(const GdPeerTable t, long long g4_per_rank, long long g4_total, long long r4_per_rank, long long r4_total,
+                 unsigned epoch, unsigned* __restrict__ counter) {
+  __shared__ bool s_last;
+  if (blockIdx.x == 0) peer_signal(t, 0, epoch);   // stream order: this rank's backward has retired, its buffers are final
+  peer_wait(t, 0, epoch);
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < g4_per_rank) {
+    const long long e = (long long)t.rank * g4_per_rank + i;
+    if (e < g4_total) {
+      float4 acc;
+      if (t.mc_grad) {   // NVLS: the switch reduces the W copies and broadcasts the sum
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(t.mc_grad + 4 * e) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(t.mc_red_grad + 4 * e), "f"(acc.x), "f"(acc.y),
+                     "f"(acc.z), "f"(acc.w) : "memory");
+      } else {
+        float4 v[GD_MAX_PEERS];
+#pragma unroll
+        for (int w = 0; w < GD_MAX_PEERS; w++)
+          if (w < t.world) v[w] = ld_peer4(t.grad[w] + 4 * e);
+        acc = v[0];
+#pragma unroll
+        for (int w = 1; w < GD_MAX_PEERS; w++)
+          if (w < t.world) { acc.x += v[w].x; acc.y += v[w].y; acc.z += v[w].z; acc.w += v[w].w; }
+#pragma unroll
+        for (int w = 0; w < GD_MAX_PEERS; w++)
+          if (w < t.world) *reinterpret_cast<float4*>(t.red_grad[w] + 4 * e) = acc;
+      }
+    }
+  } else if (i - g4_per_rank < r4_per_rank) {
+    const long long e = (long long)t.rank * r4_per_rank + (i - g4_per_rank);
+    if (e < r4_total) {
+      int4 m = ld_peer4i(t.radii[0] + 4 * e);
+      for (int w = 1; w < t.world; w++) {
+        const int4 v = ld_peer4i(t.radii[w] + 4 * e);
+        m.x = max(m.x, v.x); m.y = max(m.y, v.y); m.z = max(m.z, v.z); m.w = max(m.w, v.w);
+      }
+      for (int w = 0; w < t.world; w++) *reinterpret_cast<int4*>(t.red_radii[w] + 4 * e) = m;
+    }
+  }
+  // the last CTA of this rank tells every peer that slice `rank` has landed in its reduced buffer
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    s_last = prev == gridDim.x - 1;
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last) peer_signal(t, 1, epoch);
+}
+__global__ void __launch_bounds__(256)
+k_params_adam_peers(int P, float* __restrict__ xyz, float* __restrict__ f_dc, float* __restrict__ opacity,
+                    float* __restrict__ scaling, float* __restrict__ rotation, const GdPeerTable t, unsigned epoch,
+                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, AdamHyper h, int densify,
+                    float* __restrict__ xyz_gradient_accum, float* __restrict__ denom, float* __restrict__ max_radii2D) {
+  peer_wait(t, 1, epoch);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float* grad = t.red_grad[t.rank];
+  if (densify) {
+    const int r = t.red_radii[t.rank][i];
+    if (r > 0) {
+      const float gx = grad[14 * (size_t)P + 3 * (size_t)i], gy = grad[14 * (size_t)P + 3 * (size_t)i + 1];
+      xyz_gradient_accum[i] += sqrtf(gx * gx + gy * gy);
+      denom[i] += 1.0f;
+      max_radii2D[i] = fmaxf(max_radii2D[i], (float)r);
+    }
+  }
+  adam_one(i, P, xyz, f_dc, opacity, scaling, rotation, grad, exp_avg, exp_avg_sq, h);
 }
 
 }  // namespace gd

@@ -253,6 +253,43 @@ int gd_densify_stats(int P, int B, const float* dmeans2D_sum, const int* radii, 
   return GD_OK;
 }
 
+static int check_peer_table(const GdPeerTable* t, const char* what) {
+  if (!t || t->world < 1 || t->world > GD_MAX_PEERS || t->rank < 0 || t->rank >= t->world) return fail(GD_ERR_INVALID_ARG, what);
+  for (int w = 0; w < t->world; w++)
+    if (!t->grad[w] || !t->radii[w] || !t->red_grad[w] || !t->red_radii[w] || !t->flags[w]) return fail(GD_ERR_INVALID_ARG, what);
+  if ((t->mc_grad == nullptr) != (t->mc_red_grad == nullptr)) return fail(GD_ERR_INVALID_ARG, what);
+  return GD_OK;
+}
+int gd_peer_allreduce(int P, const GdPeerTable* t, unsigned epoch, unsigned* counter, gd_stream_t stream) {
+  if (P < 1 || !counter || epoch == 0) return fail(GD_ERR_INVALID_ARG, "peer_allreduce: P >= 1, counter and a non-zero epoch required%s");
+  const int rc = check_peer_table(t, "peer_allreduce: bad peer table%s");
+  if (rc != GD_OK) return rc;
+  const long long g4_total = (17LL * P + 3) / 4, r4_total = ((long long)P + 3) / 4;
+  const long long g4 = (g4_total + t->world - 1) / t->world, r4 = (r4_total + t->world - 1) / t->world;
+  const long long blocks = (g4 + r4 + 255) / 256;
+  gd::k_peer_allreduce<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*t, g4, g4_total, r4, r4_total, epoch, counter);
+  GD_LAUNCH_CHECK("k_peer_allreduce");
+  return GD_OK;
+}
+int gd_params_adam_peers(int P, float* xyz, float* f_dc, float* opacity, float* scaling, float* rotation, const GdPeerTable* t,
+                         unsigned epoch, float* exp_avg, float* exp_avg_sq, const float* lr5, float beta1, float beta2, float eps,
+                         int step, int densify, float* xyz_gradient_accum, float* denom, float* max_radii2D, gd_stream_t stream) {
+  if (P < 1 || step < 1 || !lr5 || !xyz || !f_dc || !opacity || !scaling || !rotation || !exp_avg || !exp_avg_sq || epoch == 0)
+    return fail(GD_ERR_INVALID_ARG, "params_adam_peers: null pointer, step < 1 or epoch 0%s");
+  if (densify && (!xyz_gradient_accum || !denom || !max_radii2D)) return fail(GD_ERR_INVALID_ARG, "params_adam_peers: statistics buffers required%s");
+  const int rc = check_peer_table(t, "params_adam_peers: bad peer table%s");
+  if (rc != GD_OK) return rc;
+  gd::AdamHyper h;
+  for (int k = 0; k < 5; k++) h.lr[k] = lr5[k];
+  h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
+  h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  h.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  gd::k_params_adam_peers<<<(P + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      P, xyz, f_dc, opacity, scaling, rotation, *t, epoch, exp_avg, exp_avg_sq, h, densify, xyz_gradient_accum, denom, max_radii2D);
+  GD_LAUNCH_CHECK("k_params_adam_peers");
+  return GD_OK;
+}
+
 int gd_sparsity_grad(long long n, long long n_total, const float* depth, const float* depth_max, float lambda,
                      float* dL_ddepth, float* scratch, float* stats, gd_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

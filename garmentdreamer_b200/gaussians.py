@@ -141,6 +141,19 @@ class GaussianParams:
                                          self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), lr, beta1, beta2, eps,
                                          self.step_count, torch.cuda.current_stream().cuda_stream), "gd_params_adam")
 
+    def adam_step_peers(self, px, densify=True, beta1=0.9, beta2=0.999, eps=1e-15):
+        """Multi-GPU form of add_densification_stats + adam_step: consumes the reduced buffers of a
+        parallel.PeerExchange whose allreduce() was launched on this stream (waits on the peers' flags on the device)."""
+        if self.exp_avg is None:
+            raise RuntimeError("call training_setup() first")
+        self.step_count += 1
+        lr = (ctypes.c_float * 5)(*self.lrs)
+        _chk(px.L.gd_params_adam_peers(self.P, self._xyz.data_ptr(), self._features_dc.data_ptr(), self._opacity.data_ptr(),
+                                       self._scaling.data_ptr(), self._rotation.data_ptr(), ctypes.byref(px.table), px.epoch,
+                                       self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), lr, beta1, beta2, eps, self.step_count,
+                                       int(densify), self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(),
+                                       self.max_radii2D.data_ptr(), torch.cuda.current_stream().cuda_stream), "gd_params_adam_peers")
+
     # ---- gaussian_model.py:415-419 + GaussianDreamer.py:263-279 -----------------------------------
     def add_densification_stats(self, viewspace_point_grad_sum, radii):
         """viewspace_point_grad_sum [P,3]: sum over the views of dL/dmeans2D; radii i32 [B,P]."""

@@ -208,6 +208,36 @@ int gd_sparsity_finish(long long n, long long n_total, const float* depth, const
 /* out[i] = max over the B views of radii[b][i] (visibility / max_radii2D bookkeeping of a view batch) */
 int gd_radii_max(int P, int B, const int* radii, int* out, gd_stream_t stream);
 
+/* ---- Multi-GPU gradient exchange over peer memory, fused with the optimiser step (SURVEY.md s.8 row e) ----
+ * The reference is single-GPU; here the view batch is sharded over W <= GD_MAX_PEERS ranks of one NVLink domain and the
+ * per-Gaussian results of every rank's rasteriser backward are summed before Adam (what autograd's accumulation over the
+ * per-view loop of TS/systems/GaussianDreamer.py:189-219 does inside one process). Every pointer in GdPeerTable is a
+ * DEVICE address valid on THIS rank: entry w points into rank w's symmetric allocation (peer-mapped), entry `rank` is local.
+ *   grad[w]      fp32 [17P padded to 4]: 14P packed parameter gradients | 3P viewspace gradients (gd_raster_backward output)
+ *   radii[w]     i32  [P padded to 4]:   per-Gaussian maximum screen radius over that rank's views (gd_radii_max)
+ *   red_grad[w] / red_radii[w]           same shapes; after gd_peer_allreduce on ALL ranks they hold SUM / MAX over ranks
+ *   flags[w]     u32  [2][GD_MAX_PEERS]  arrival epochs, zero-initialised; epoch must increase by one per call pair
+ *   mc_grad / mc_red_grad                NVLS multicast addresses of grad / red_grad (NULL: peer loads and stores instead)
+ * gd_peer_allreduce: cross-rank barrier (entry), reduce-scatter + all-gather of both arrays. counter: LOCAL u32, zero.
+ * gd_params_adam_peers: waits for every rank's slice, then gd_densify_stats (if densify; B = 1 on red_radii) and
+ *   gd_params_adam on red_grad[rank] in one kernel. Both are asynchronous on `stream`; no host synchronisation. */
+#define GD_MAX_PEERS 8
+typedef struct {
+  int world, rank;
+  const float* grad[GD_MAX_PEERS];
+  const int* radii[GD_MAX_PEERS];
+  float* red_grad[GD_MAX_PEERS];
+  int* red_radii[GD_MAX_PEERS];
+  unsigned* flags[GD_MAX_PEERS];
+  const float* mc_grad;
+  float* mc_red_grad;
+} GdPeerTable;
+int gd_peer_allreduce(int P, const GdPeerTable* t, unsigned epoch, unsigned* counter, gd_stream_t stream);
+int gd_params_adam_peers(int P, float* xyz, float* f_dc, float* opacity, float* scaling, float* rotation,
+                         const GdPeerTable* t, unsigned epoch, float* exp_avg, float* exp_avg_sq, const float* lr5,
+                         float beta1, float beta2, float eps, int step, int densify, float* xyz_gradient_accum,
+                         float* denom, float* max_radii2D, gd_stream_t stream);
+
 /* Batched camera construction: replaces Camera.__init__ (GS/scene/cameras.py:50-53,
  * GS/utils/graphics_utils.py:59-101), which the reference runs on the CPU per view per iteration.
  * c2w: DEVICE fp32 [B,4,4] row-major camera-to-world (batch['c2w_3dgs']); tan_half_fovx/y: HOST

@@ -137,3 +137,49 @@ def test_changing_P_between_steps_resizes_every_buffer():
     a.gaussian = make(1200)              # "pruned"
     a.training_step(batch)
     assert a.grad.numel() == 17 * 1200 and torch.isfinite(a.grad).all()
+
+
+def test_peer_exchange_world1_matches_plain_adam():
+    """parallel.PeerExchange (gd_peer_allreduce + gd_params_adam_peers) on a one-rank group: flags, slices, padding (P % 4 != 0)
+    and the fused statistics + Adam kernel against gd_densify_stats + gd_params_adam. (N > 1: tools/peer_exchange_check.py,
+    profiles/r02_peer_exchange_n*.json.)"""
+    import os
+    import torch.distributed as dist
+    from garmentdreamer_b200 import parallel
+    from garmentdreamer_b200.gaussians import GaussianParams
+    from garmentdreamer_b200.synthetic import garment, raw_params
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        P = 7001
+        dev = torch.device("cuda", 0)
+        try:
+            px = parallel.PeerExchange(P, dev)
+        except Exception as e:   # noqa: BLE001
+            pytest.skip(f"symmetric memory unavailable here: {e}")
+        raw = {k: v.to(dev) for k, v in raw_params(garment(P, 0)).items()}
+        mk = lambda: GaussianParams(raw["xyz"], raw["f_dc"], raw["opacity"], raw["scaling"], raw["rotation"], spatial_lr_scale=4.0)
+        ga, gb = mk(), mk()
+        ga.training_setup(); gb.training_setup()
+        for step in range(3):
+            g = torch.Generator(device=dev).manual_seed(step)
+            grad = torch.randn(17 * P, generator=g, device=dev) * 1e-3
+            radii = torch.randint(0, 40, (P,), generator=g, device=dev, dtype=torch.int32)
+            px.grad.copy_(grad); px.radii.copy_(radii)
+            ga.update_learning_rate(step); gb.update_learning_rate(step)
+            ga.add_densification_stats(grad[14 * P:].view(P, 3), radii.view(1, P))
+            ga.adam_step(grad[:14 * P])
+            px.allreduce()
+            gb.adam_step_peers(px)
+            torch.cuda.synchronize()
+            assert torch.equal(px.red_grad, grad) and torch.equal(px.red_radii, radii)
+            for a, b in ((ga._xyz, gb._xyz), (ga._features_dc, gb._features_dc), (ga._opacity, gb._opacity), (ga._scaling, gb._scaling),
+                         (ga._rotation, gb._rotation), (ga.exp_avg, gb.exp_avg), (ga.exp_avg_sq, gb.exp_avg_sq),
+                         (ga.xyz_gradient_accum, gb.xyz_gradient_accum), (ga.denom, gb.denom), (ga.max_radii2D, gb.max_radii2D)):
+                assert torch.equal(a, b)
+    finally:
+        if created:
+            dist.destroy_process_group()
