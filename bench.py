@@ -362,7 +362,7 @@ def main():
     sampler.join(timeout=2)
     e2e_ms = sum(x.elapsed_time(y) for x, y in t_e2e)
     # ---- the collective alone (after a barrier: no rank skew in it) ----
-    ar_us = None
+    ar_us = px_us = None
     if world > 1:
         buf = torch.zeros_like(system.grad)
         for _ in range(3):
@@ -375,6 +375,20 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ar_us = e0.elapsed_time(e1) / 10 * 1e3
+        px_us = None
+        if getattr(system, "peers", None) is not None:   # the exchange the step really uses: peer memory, fused with Adam
+            px, g = system.peers, system.gaussian
+            step0 = g.step_count
+            for _ in range(3):
+                px.allreduce(); g.adam_step_peers(px, densify=False)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                px.allreduce(); g.adam_step_peers(px, densify=False)
+            e1.record()
+            torch.cuda.synchronize()
+            px_us = e0.elapsed_time(e1) / 10 * 1e3
     t = torch.tensor([dev_ms, e2e_ms, phases["allreduce"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -429,8 +443,11 @@ def main():
         "phase_ms": phases,
     }
     if world > 1:
-        line["allreduce_us"] = {"isolated_after_barrier": ar_us, "inside_step_incl_rank_skew_max_over_ranks": ar_phase_ms * 1e3,
-                                "bytes": int(system.grad.numel() * 4 + system.radii_max.numel() * 4)}
+        line["allreduce_us"] = {"nccl_allreduce_isolated_after_barrier": ar_us, "inside_step_incl_rank_skew_max_over_ranks": ar_phase_ms * 1e3,
+                                "bytes": int(system.grad.numel() * 4 + system.radii_max.numel() * 4),
+                                "path": "peer memory (gd_peer_allreduce + gd_params_adam_peers)" if px_us is not None else "nccl",
+                                "peer_exchange_plus_adam_isolated_after_barrier": px_us,
+                                "multicast": bool(system.peers.multicast) if px_us is not None else None}
     if not a.no_gpu_reference and world == 1:
         cams = sample_cameras(Btot, S, S)[lo:hi]
         for c in cams:
