@@ -54,6 +54,8 @@ struct GemmKParams {
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
   float* colstats;            // optional [ceil(M/32)][2][N]: per 32-row block and output column, sum and sum of squares of the fp16
                               // values this GEMM stores (GroupNorm statistics of the consumer without another pass over the tensor)
+  const float4* gn_coef;      // MODE 4 (GroupNorm-backward producer): [images][N] (ya, yb, ca, cb); p.residual = the GroupNorm input x.
+                              // The epilogue stores g = acc * silu'(x*ya + yb) and colstats = per 32-row block sum g | sum g*(x*ca + cb)
   int a_halo;                 // CTA pairs, 3x3 conv on rows of >= 128 pixels: ONE haloed A tile (130 pixels x 64 ch) per (dy, channel
                               // block) serves the three dx taps through row-shifted UMMA descriptors (A traffic / 3)
 };
@@ -169,13 +171,22 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// silu'(y) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): ONE SFU op (tanh.approx, |rel err| <= 2^-11, below the fp16 rounding of
+// the result) instead of ex2 + rcp
+__device__ __forceinline__ float dsilu_tanh(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  const float s = fmaf(0.5f, t, 0.5f);
+  return s * fmaf(y, 1.0f - s, 1.0f);
+}
 
 // Persistent, warp-specialised: grid = min(tiles, SMs). The accumulator is double-buffered in
 // TMEM so the epilogue of tile i overlaps the main loop of tile i+1; the TMA ring runs ahead
 // across tile boundaries. 10 warps: 0 = TMA producer, 1 = MMA issuer (+TMEM owner), 2..9 =
 // epilogue (two warps per TMEM lane quarter, each takes half of the tile's 32-column chunks).
 // MODE: 0 plain epilogue (bias / time-embedding / residual / SiLU), 1 GEGLU, 2 transposed store,
-// 3 split-K fp32 partials. One instantiation per mode keeps each kernel's code small (I-cache).
+// 3 split-K fp32 partials, 4 plain + GroupNorm-backward producer (the data-gradient GEMM in front of a GroupNorm+SiLU
+// backward multiplies its output by silu'(y) and emits the two column sums that backward needs: no statistics sweep). One instantiation per mode keeps each kernel's code small (I-cache).
 // TWO: CTA-pair version (launched as clusters of 2): tile = 256 x BLOCK_N, per-CTA operand traffic
 // 128 x 64 of A + BLOCK_N/2 x 64 of B per k-block instead of 128 x 64 + BLOCK_N x 64.
 template <int MODE, bool TWO>
@@ -379,14 +390,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // accumulator (bias + time-embedding bias -> per-warp shared memory, residual -> registers) is
     // fetched BEFORE waiting for the MMA, so the global-load latency hides behind the main loop.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    constexpr bool geglu = MODE == 1, transposed = MODE == 2, splitk = MODE == 3;
+    constexpr bool geglu = MODE == 1, transposed = MODE == 2, splitk = MODE == 3, gnb = MODE == 4;
+    constexpr bool plain = MODE == 0 || MODE == 4;
     const int chunks = (BN + 31) / 32;
     float* sb = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * p.bias_stride;   // [chunks of this warp][32] bias sums
+    // MODE 4: (ya, yb, ca, cb) of this warp's columns, behind the bias area: [4 chunks][32] float4 per warp (host reserves it)
+    float4* sgn = reinterpret_cast<float4*>(reinterpret_cast<float*>(tmem_slot + 4) + kEpiWarps * p.bias_stride) + (warp - 2) * 128;
     // output staging for the TMA store: 2 x [32 rows x 64 B] per warp, 64B-swizzled, 1024-aligned
     uint8_t* stg_base = stg_all + (size_t)(warp - 2) * p.stg_bufs * 2048;
     uint32_t st_cnt = 0;
-    if (MODE == 0 && p.tma_store && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    const bool vec_ok = (p.ldc & 7) == 0 && MODE == 0;
+    if (plain && p.tma_store && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    const bool vec_ok = (p.ldc & 7) == 0 && plain;
     int lt = 0;
     for (int t = tile0; t < total; t += tile_step, lt++) {
       const int ks = t % p.ksplit, tt = t / p.ksplit;
@@ -411,6 +425,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.row_bias && m_blk * kBM < p.M) bsum += __half2float(p.row_bias[(long long)img * p.row_bias_ld + n]);
         }
         sb[ci * 32 + lane] = bsum;
+        if constexpr (gnb) {   // one coalesced 512-byte load per chunk; the math loop reads them back as broadcasts
+          const bool on = half + 2 * ci < chunks && n < nlim && m_blk * kBM < p.M;
+          sgn[ci * 32 + lane] = on ? __ldg(p.gn_coef + (size_t)img * p.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       // residual of the warp's first chunk now, of chunk c+2 while chunk c is processed (rolled
       // loop: unrolling the chunk body 4x made the kernel 258 KB of SASS and thrashed the I-cache)
@@ -457,7 +475,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n0 >= nlim) continue;                 // warp-uniform
         if (p.flags & GD_EPI_PROBE_SKIP) continue;   // timing experiment only: epilogue math + stores skipped
         const bool full32 = n0 + 32 <= nlim;
-        if (!(MODE == 0 && p.tma_store && full32) && !row_ok) continue;   // the staged paths need the whole warp
+        if (!(plain && p.tma_store && full32) && !row_ok) continue;   // the staged paths need the whole warp
         if constexpr (splitk) {  // raw fp32 partial sums; bias / residual / rounding happen in the finalize kernel
           float* wdst = p.ws + ((size_t)ks * p.M + row) * p.N + n0;
           if (full32) {
@@ -498,14 +516,36 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __half* dst = p.C + coff + (long long)row * p.ldc + n0;
           if (full32 && (p.ldc & 7) == 0) {
             uint4 o[4];
-            if (p.residual) {
+            uint4 ox[4];   // gnb: xh = (x - mean) * rstd of the same elements, fp16 (second staging tile)
+            if constexpr (gnb) {
               const __half* rh = reinterpret_cast<const __half*>(&rcur[0]);
+              const float4* cf = sgn + ci * 32;   // broadcast LDS.128 per column
 #pragma unroll
-              for (int j = 0; j < 32; j++) v[j] += __half2float(rh[j]);
-            }
-            if (p.flags & GD_EPI_SILU) {
+              for (int u = 0; u < 4; u++) {
+                float xh[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                  const int j = 8 * u + k;
+                  const float4 c4 = cf[j];
+                  const float xf = __half2float(rh[j]);
+                  v[j] *= dsilu_tanh(fmaf(xf, c4.x, c4.y));
+                  xh[k] = fmaf(xf, c4.z, c4.w);
+                }
+                __half2 h0 = __floats2half2_rn(xh[0], xh[1]), h1 = __floats2half2_rn(xh[2], xh[3]);
+                __half2 h2 = __floats2half2_rn(xh[4], xh[5]), h3 = __floats2half2_rn(xh[6], xh[7]);
+                ox[u] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+            } else {
+              if (p.residual) {
+                const __half* rh = reinterpret_cast<const __half*>(&rcur[0]);
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] += __half2float(rh[j]);
+              }
+              if (p.flags & GD_EPI_SILU) {
 #pragma unroll 4
-              for (int j = 0; j < 32; j++) v[j] = silu(v[j]);
+                for (int j = 0; j < 32; j++) v[j] = silu(v[j]);
+              }
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -523,6 +563,11 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int u = 0; u < 4; u++)
                 *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o[u];
+              if constexpr (gnb) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                  *reinterpret_cast<uint4*>(stg + 2048 + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = ox[u];
+              }
               __syncwarp();
               const int piece = lane & 3;
               const int row0 = m_blk * kBM + q * 32;
@@ -535,7 +580,16 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
                 if (row0 + r < p.M) {
                   *reinterpret_cast<uint4*>(p.C + coff + (long long)(row0 + r) * p.ldc + n0 + piece * 8) = val;
-                  if (p.colstats) {
+                  if constexpr (gnb) {   // sum g | sum g * xh (the GroupNorm backward's two reductions)
+                    const uint4 valx = *reinterpret_cast<const uint4*>(stg + 2048 + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
+                    const __half2* hv = reinterpret_cast<const __half2*>(&val);
+                    const __half2* hx = reinterpret_cast<const __half2*>(&valx);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                      const float2 f = __half22float2(hv[u]), x2 = __half22float2(hx[u]);
+                      cs[2 * u] += f.x; cq[2 * u] = fmaf(f.x, x2.x, cq[2 * u]); cs[2 * u + 1] += f.y; cq[2 * u + 1] = fmaf(f.y, x2.y, cq[2 * u + 1]);
+                    }
+                  } else if (p.colstats) {
                     const __half2* hv = reinterpret_cast<const __half2*>(&val);
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
@@ -615,7 +669,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  if (MODE == 0 && warp >= 2) {
+  if ((MODE == 0 || MODE == 4) && warp >= 2) {
     if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging reads + writes done
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -352,7 +352,7 @@ __device__ __forceinline__ void colstats_fold_source(const float* __restrict__ s
 }
 __global__ void __launch_bounds__(256)
 k_gn_colstats_reduce(const float* __restrict__ statsA, int Ca, const float* __restrict__ statsB, int Cb, int rb_per_image,
-                     int groups, int splits, float2* __restrict__ part) {
+                     int groups, int splits, float2* __restrict__ part, const __half* __restrict__ gamma) {
   pdl_entry();
   __shared__ __align__(16) float s_lane[1024];   // lanes * 2 * Cs <= 1024 floats when Cs <= 512
   __shared__ float s_tot[2 * 2560];              // [sum | sumsq][C]
@@ -364,9 +364,25 @@ k_gn_colstats_reduce(const float* __restrict__ statsA, int Ca, const float* __re
   if ((int)threadIdx.x < groups) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += s_tot[c]; b += s_tot[C + c]; }
+    for (int c = g * cpg; c < (g + 1) * cpg; c++) {
+      const float w = gamma ? __half2float(gamma[c]) : 1.0f;   // backward: sum_c gamma_c * (sum g | sum g xh)
+      a = fmaf(s_tot[c], w, a); b = fmaf(s_tot[C + c], w, b);
+    }
     part[((size_t)n * groups + g) * splits + sp] = make_float2(a, b);
   }
+}
+// GroupNorm-backward coefficient table for the MODE 4 GEMM epilogue: per (image, channel) (ya, yb, ca, cb) with
+// xh = x*ca + cb = (x - mean) * rstd and y = x*ya + yb = xh*gamma + beta.
+__global__ void __launch_bounds__(256)
+k_gn_bwd_coef(const float2* __restrict__ stats, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+              float4* __restrict__ coef, int N, int C, int groups) {
+  pdl_entry();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  const float2 mr = stats[(size_t)n * groups + c / (C / groups)];
+  const float ca = mr.y, cb = -mr.x * mr.y, g = __half2float(gamma[c]);
+  coef[i] = make_float4(ca * g, fmaf(cb, g, __half2float(beta[c])), ca, cb);
 }
 
 // ---- LayerNorm: one warp per row -----------------------------------------------------------
@@ -761,6 +777,8 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     }
     if (geglu && BN % 32) BN = (BN + 31) / 32 * 32;
   }
+  if (a->gn_coef && (!a->colstats || !a->residual))
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: the GroupNorm-backward epilogue needs colstats and residual (= the GroupNorm input)");
   if (BN % 16 || BN < 16 || BN > 256 || ((a->flags & GD_EPI_GEGLU) && BN % 32))
     return fail(GD_UNET_ERR_INVALID_ARG, "gemm: block_n must be a multiple of 16 in 16..256");
 
@@ -831,17 +849,24 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   // one persistent CTA per SM owns the shared memory: operand ring + epilogue staging + barriers/bias
   const int bias_stride = 32 * ((((BN + 31) / 32) + 1) / 2);   // bias floats per epilogue warp
   p.bias_stride = bias_stride;
-  const size_t smem_max = 227 * 1024, fixed_noslack = 256 + 64 + (size_t)gdu::kEpiWarps * bias_stride * sizeof(float);
+  const size_t smem_max = 227 * 1024, fixed_noslack = 256 + 64 + (size_t)gdu::kEpiWarps * bias_stride * sizeof(float) +
+                                                     (a->gn_coef ? (size_t)gdu::kEpiWarps * 128 * sizeof(float4) : 0);   // MODE 4 coefficient staging
   const size_t fixed = 1024 + fixed_noslack;
   const bool mode0 = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED));
   const bool tma_ok = mode0 && (a->ldc % 8) == 0 && (a->c_batch_stride % 8) == 0 && (a->c_head_stride % 8) == 0 &&
                       ((uintptr_t)a->C % 16) == 0 && (a->heads == 1 || a->c_head_stride > 0) &&
                       (a->batch == a->heads || a->c_batch_stride > 0);
   static const bool use_tma_store = []() { const char* e = getenv("GD_GEMM_TMA_STORE"); return e && e[0] == '1'; }();
-  int stg_bufs = tma_ok ? (use_tma_store ? 2 : 1) : 0;   // the synchronous staged store needs one buffer per warp
+  // GroupNorm-backward producer epilogue (MODE 4): CTA pairs, staged synchronous store, whole 32-column chunks, one image per
+  // 32-row block. When the shape does not allow it the GEMM runs plain (residual ignored) and returns GD_UNET_NO_COLSTATS.
+  const bool gnb = a->gn_coef && two && ksplit == 1 && mode0 && tma_ok && !use_tma_store && !(a->flags & GD_EPI_SILU) && a->N % 32 == 0 &&
+                   BN % 32 == 0 && a->batch == 1 && a->rows_per_image > 0 && a->rows_per_image % 32 == 0;
+  if (a->gn_coef && !gnb) p.residual = nullptr;
+  p.gn_coef = gnb ? reinterpret_cast<const float4*>(a->gn_coef) : nullptr;
+  int stg_bufs = tma_ok ? ((use_tma_store || gnb) ? 2 : 1) : 0;   // the synchronous staged store needs one buffer per warp (two: g | xh)
   int stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
   if (tma_ok && stages < 4) {
-    stg_bufs = 1;
+    stg_bufs = gnb ? 2 : 1;   // (the GroupNorm-backward epilogue stages two tiles per chunk: g and xh)
     stages = (int)((smem_max - fixed - (size_t)gdu::kEpiWarps * stg_bufs * 2048) / stage_bytes);
   }
   // CTA pairs whose B tile is the same for every output tile (one N tile, no batch): keep this CTA's half of B
@@ -899,8 +924,9 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     p.tma_store = use_tma_store ? 1 : 2;
   }
   // fused GroupNorm column statistics need the staged store path and whole 32-column chunks
-  const bool colstats_ok = a->colstats && p.tma_store == 2 && a->N % 32 == 0 && BN % 32 == 0 && a->batch == 1;
+  const bool colstats_ok = a->colstats && p.tma_store == 2 && a->N % 32 == 0 && BN % 32 == 0 && a->batch == 1 && (!a->gn_coef || gnb);
   p.colstats = colstats_ok ? reinterpret_cast<float*>(a->colstats) : nullptr;
+  if (gnb && !colstats_ok) return fail(GD_UNET_ERR_INVALID_ARG, "gemm: internal: GroupNorm-backward epilogue without column statistics");
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -913,7 +939,8 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
         cudaFuncSetAttribute(gdu::k_gemm_tcgen05<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
         cudaFuncSetAttribute(gdu::k_gemm_tcgen05<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
         cudaFuncSetAttribute(gdu::k_gemm_tcgen05<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
+        cudaFuncSetAttribute(gdu::k_gemm_tcgen05<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
       return fail(GD_UNET_ERR_CUDA, "gemm: cannot raise dynamic shared memory limit");
   }
   const dim3 blk(gdu::kGemmThreads);
@@ -923,6 +950,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     const dim3 grid(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
     if (a->flags & GD_EPI_GEGLU) launch_pdl_cluster(2, gdu::k_gemm_tcgen05<1, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
     else if (a->flags & GD_EPI_TRANSPOSED) launch_pdl_cluster(2, gdu::k_gemm_tcgen05<2, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
+    else if (gnb) launch_pdl_cluster(2, gdu::k_gemm_tcgen05<4, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
     else launch_pdl_cluster(2, gdu::k_gemm_tcgen05<0, true>, grid, blk, smem, stream, tmA, tmB, tmC, p);
   } else {
     const dim3 grid(p.total_tiles < num_sms ? p.total_tiles : num_sms);
@@ -1219,7 +1247,7 @@ int gd_unet_groupnorm_colstats(const void* x, void* y, const void* gamma, const 
   while ((size_t)N * groups * splits > cap && splits > 1) splits /= 2;
   if ((size_t)N * groups * splits > cap) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_colstats: N * groups exceeds the scratch");
   launch_pdl(gdu::k_gn_colstats_reduce, dim3(N, (unsigned)splits), dim3(256), (size_t)0, s, statsA, Ca, statsB, Cb, rbpi, groups,
-             (int)splits, part);
+             (int)splits, part, (const __half*)nullptr);
   LAUNCH_CHECK("k_gn_colstats_reduce");
   if (mean_rstd) {   // VAE flavour: (mean, rstd) table kept for the backward, fast sweeps
     const int total = N * groups;
@@ -1233,6 +1261,58 @@ int gd_unet_groupnorm_colstats(const void* x, void* y, const void* gamma, const 
   launch_pdl(gdu::k_gn_apply, dim3(N, (HW + pix_per_cta - 1) / pix_per_cta), dim3(256), (size_t)(sizeof(float2) * C), s, (const __half*)x,
              (__half*)y, (const float2*)part, (const __half*)gamma, (const __half*)beta, HW, C, groups, (int)splits, eps, silu, pix_per_cta);
   LAUNCH_CHECK("k_gn_apply");
+  return GD_UNET_OK;
+}
+
+int gd_unet_gn_bwd_coef(const float* stats, const void* gamma, const void* beta, float* coef, int N, int C, int groups, gd_ustream_t s_) {
+  if (!stats || !gamma || !beta || !coef || N < 1 || C < 1 || groups < 1 || C % groups)
+    return fail(GD_UNET_ERR_INVALID_ARG, "gn_bwd_coef: bad argument");
+  launch_pdl(gdu::k_gn_bwd_coef, dim3((unsigned)((N * C + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s_, (const float2*)stats,
+             (const __half*)gamma, (const __half*)beta, (float4*)coef, N, C, groups);
+  LAUNCH_CHECK("k_gn_bwd_coef");
+  return GD_UNET_OK;
+}
+int gd_unet_groupnorm_bwd_g(const void* x, const void* g, const void* add, void* dx, const void* gamma, const void* beta,
+                            const float* stats, const float* colstats, int N, int HW, int C, int groups, gd_ustream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (!x || !g || !dx || !gamma || !beta || !stats || !colstats) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd_g: null pointer");
+  if (C % groups || C % 8 || N * groups > 8192 || groups > 256 || C > 2048 || HW % 32)
+    return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd_g: C % groups == 0, C % 8 == 0, C <= 2048, HW % 32 == 0");
+  float2* part = gn_part_buffer();
+  if (!part) return fail(GD_UNET_ERR_CUDA, "groupnorm_bwd_g: cudaMalloc");
+  float2* bstats = device_scratch()->gn_bstats;
+  const int rbpi = HW / 32;
+  long long splits = ((long long)rbpi * (C / 2) + 2047) / 2048;
+  if (splits > 512) splits = 512;
+  while (N * splits < 296 && splits * 2 <= rbpi && splits < 512) splits *= 2;
+  if (splits > rbpi) splits = rbpi;
+  if (splits < 1) splits = 1;
+  if ((size_t)N * groups * splits > kGnBig) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd_g: N * groups * splits exceeds the scratch");
+  launch_pdl(gdu::k_gn_colstats_reduce, dim3(N, (unsigned)splits), dim3(256), (size_t)0, s, colstats, C, (const float*)nullptr, 0, rbpi,
+             groups, (int)splits, part, (const __half*)gamma);
+  LAUNCH_CHECK("k_gn_colstats_reduce");
+  const int total = N * groups;
+  launch_pdl(gdu::k_gn_bwd_finalize, dim3((total + 7) / 8), dim3(256), (size_t)0, s, (const float2*)part, bstats, total, (int)splits,
+             1.0f / ((float)HW * (float)(C / groups)));
+  LAUNCH_CHECK("k_gn_bwd_finalize");
+  // g already carries silu'(y): the plain (no-activation) apply sweep finishes dx = rstd*(gamma*g - S1 - xh*S2) (+ add)
+  if (256 % (C / 8) == 0) {
+    const int pix_per_cta = gn_fast_pix_per_cta(N, HW, C, 2);
+    const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+    if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd_g: image too large");
+    launch_pdl(gdu::k_gn_bwd_apply_fast<false, 2>, dim3(N, (unsigned)chunks), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)g,
+               (const __half*)add, (__half*)dx, (const float2*)stats, (const float2*)bstats, (const __half*)gamma,
+               (const __half*)beta, HW, C, groups, pix_per_cta);
+    LAUNCH_CHECK("k_gn_bwd_apply_fast");
+    return GD_UNET_OK;
+  }
+  const int pix_per_cta = (32768 + C - 1) / C;
+  const long long chunks = ((long long)HW + pix_per_cta - 1) / pix_per_cta;
+  if (chunks > 65535) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd_g: image too large");
+  launch_pdl(gdu::k_gn_bwd_apply, dim3(N, (unsigned)chunks), dim3(256), (size_t)((sizeof(float4) + sizeof(float2)) * C), s, (const __half*)x,
+             (const __half*)g, (const __half*)add, (__half*)dx, (const float2*)stats, (const float2*)bstats, (const __half*)gamma,
+             (const __half*)beta, HW, C, groups, 0, pix_per_cta);
+  LAUNCH_CHECK("k_gn_bwd_apply");
   return GD_UNET_OK;
 }
 

@@ -70,14 +70,7 @@ k_gn_apply_final(const __half* __restrict__ x, __half* __restrict__ y, const flo
 // z = act(GN(x)), upstream dz. With xh = (x - mean) * rstd, y = xh*gamma + beta,
 // g = dz * act'(y):   dx = rstd * (gamma*g - S1 - xh*S2),  S1 = mean_group(gamma*g),
 // S2 = mean_group(gamma*g*xh).
-__device__ __forceinline__ float dsilu(float y) {
-  // sigmoid(y) = 0.5 + 0.5 tanh(y/2): ONE SFU op (tanh.approx, |rel err| <= 2^-11 -- below the fp16 rounding of the
-  // result) instead of ex2 + rcp; the GroupNorm backward sweeps were SFU/issue-bound on the two-op form.
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
-  const float s = fmaf(0.5f, t, 0.5f);
-  return s * fmaf(y, 1.0f - s, 1.0f);
-}
+__device__ __forceinline__ float dsilu(float y) { return dsilu_tanh(y); }   // one SFU op (gd_gemm.cuh)
 // Pass 1: same sweep as k_gn_stats; per channel sum(g), sum(g*xh) folded with gamma per group.
 __global__ void __launch_bounds__(256)
 k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dz, const float2* __restrict__ stats,

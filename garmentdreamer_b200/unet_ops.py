@@ -32,6 +32,7 @@ class GdGemmArgs(ctypes.Structure):
         ("alpha", ctypes.c_float), ("flags", ctypes.c_uint), ("block_n", ctypes.c_int),
         ("row_bias_ld", ctypes.c_longlong),
         ("colstats", ctypes.c_void_p),
+        ("gn_coef", ctypes.c_void_p),
     ]
 
 
@@ -99,6 +100,9 @@ def lib():
         L.gd_unet_init.restype = ctypes.c_int
         L.gd_unet_groupnorm_colstats.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, f, i, vp]
         L.gd_unet_groupnorm_colstats.restype = ctypes.c_int
+        L.gd_unet_gn_bwd_coef.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+        L.gd_unet_groupnorm_bwd_g.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
+        L.gd_unet_gn_bwd_coef.restype = L.gd_unet_groupnorm_bwd_g.restype = ctypes.c_int
         L.gd_resize_bilinear.argtypes = [vp, vp, i, i, i, i, i, vp]
         L.gd_resize_bilinear_bwd.argtypes = [vp, vp, i, i, i, i, i, vp]
         L.gd_resize_bilinear.restype = L.gd_resize_bilinear_bwd.restype = ctypes.c_int
@@ -153,6 +157,7 @@ def _gemm(a: GdGemmArgs, out=None, want_stats=False):
         _chk(rc, "gd_unet_gemm")
     if out is not None:
         out._gd_colstats = (stats, a.N) if (stats is not None and rc == 0) else None
+        out._gd_is_g = bool(a.gn_coef) and rc == 0   # the output already carries silu'(GN(x)) (GroupNorm-backward producer)
 
 
 _FUSE_GN_STATS = os.environ.get("GD_FUSE_GN_STATS", "1") != "0"
@@ -238,7 +243,7 @@ def _conv_box(H, W, N):
     return W, H, rows // H
 
 
-def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False):
+def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False, gn_bwd=None):
     """Implicit-GEMM convolution over NHWC x[N,H,W,Cx]: out[n,y,x,:] = sum_t x[n, y+dy_t, x+dx_t,
     c_t : c_t+Ck] @ w[:, t*Ck:(t+1)*Ck]^T (zero outside the image). taps = [(dx, dy, c)], w
     [Cout, len(taps)*Ck]. `out` may be a channel slice of a wider NHWC tensor."""
@@ -267,17 +272,36 @@ def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=No
     if row_bias is not None:
         a.row_bias_ld = row_bias.stride(0)
     a.alpha, a.flags = 1.0, flags
+    if gn_bwd is not None and _FUSE_GN_BWD:
+        # this GEMM is the data gradient in front of a GroupNorm+SiLU backward: gn_bwd = (x, stats, gamma, beta) of that GroupNorm
+        gx, gstats, ggamma, gbeta = gn_bwd
+        Nimg, C = gx.shape[0], gx.shape[-1]
+        coef = torch.empty((Nimg, C, 4), dtype=torch.float32, device=gx.device)
+        _chk(lib().gd_unet_gn_bwd_coef(gstats.data_ptr(), ggamma.data_ptr(), gbeta.data_ptr(), coef.data_ptr(), Nimg, C, 32, _stream()),
+             "gn_bwd_coef")
+        a.residual, a.gn_coef = _h(gx).data_ptr(), coef.data_ptr()
+        want_stats = True
+        if not _FUSE_GN_STATS:   # the column statistics are part of this epilogue
+            stats = torch.empty(((a.M + 31) // 32, 2, a.N), dtype=torch.float32, device=out.device)
+            a.colstats = stats.data_ptr()
+            rc = lib().gd_unet_gemm(ctypes.byref(a), _stream())
+            if rc not in (0, 1):
+                _chk(rc, "gd_unet_gemm")
+            out._gd_colstats = (stats, a.N) if rc == 0 else None
+            out._gd_is_g = rc == 0
+            return out
     _gemm(a, out, want_stats)
     return out
 
 
+_FUSE_GN_BWD = os.environ.get("GD_FUSE_GN_BWD", "1") != "0"
 _TAPS_3X3 = [(t % 3 - 1, t // 3 - 1, 0) for t in range(9)]
 
 
-def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False):
+def conv3x3(x, w, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False, gn_bwd=None):
     """3x3, stride 1, pad 1 over NHWC x[N,H,W,Cin]; w[Cout,3,3,Cin]."""
     return conv_taps(x, w, _TAPS_3X3, x.shape[-1], bias, row_bias=row_bias, residual=residual, out=out, flags=flags,
-                     want_stats=want_stats)
+                     want_stats=want_stats, gn_bwd=gn_bwd)
 
 
 def conv3x3_stride2(x, w, bias=None, *, s2d=None, out=None, want_stats=False):
@@ -524,8 +548,19 @@ def groupnorm_bwd(x, dz, gamma, beta, stats, groups=32, silu=False, add=None, ou
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     out = torch.empty_like(x) if out is None else out
+    cs = getattr(dz, "_gd_colstats", None)
+    if getattr(dz, "_gd_is_g", False) and cs is not None and silu and HW % 32 == 0:
+        # dz came out of a GEMM whose epilogue already applied silu'(GN(x)) and summed g | g*xh per column: no statistics sweep
+        _chk(lib().gd_unet_groupnorm_bwd_g(_h(x).data_ptr(), _h(dz).data_ptr(), _p(add), out.data_ptr(), gamma.data_ptr(),
+                                           beta.data_ptr(), stats.data_ptr(), cs[0].data_ptr(), N, HW, C, groups, _stream()),
+             "groupnorm_bwd_g")
+        out._gd_colstats, out._gd_is_g = None, False
+        return out
+    if getattr(dz, "_gd_is_g", False):
+        raise RuntimeError("groupnorm_bwd: the gradient was produced by a GroupNorm-backward GEMM epilogue but cannot be consumed here")
     _chk(lib().gd_unet_groupnorm_bwd(_h(x).data_ptr(), _h(dz).data_ptr(), _p(add), out.data_ptr(), gamma.data_ptr(),
                                      beta.data_ptr(), stats.data_ptr(), N, HW, C, groups, int(silu), _stream()), "groupnorm_bwd")
+    out._gd_colstats, out._gd_is_g = None, False
     return out
 
 

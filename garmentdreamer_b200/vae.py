@@ -31,6 +31,9 @@ GRAD_TARGET = 16.0   # the fp16 backward chain starts with max |d moments| in [8
 _DOWN_TAPS = [((kx >> 1), (ky >> 1), ((ky & 1) * 2 + (kx & 1))) for ky in range(3) for kx in range(3)]
 
 
+_GN_BWD_FUSE_MIN_C = int(__import__("os").environ.get("GD_GN_BWD_FUSE_MIN_C", "256"))
+
+
 class VAEEncoderB200:
     """encode(imgs01, noise) -> latents; backward(grad_latents) -> d imgs01 (both fp32 NCHW)."""
 
@@ -116,9 +119,13 @@ class VAEEncoderB200:
     def _resnet_bwd(self, rec, dout):
         _, p, x, st1, h1, st2 = rec
         w = self.w
-        dn2 = ops.conv3x3(dout, w[p + ".conv2.bwd"])
+        # >= 256 channels: the data-gradient GEMMs apply silu'(GN(.)) and emit the backward's column sums in their epilogue (no
+        # statistics sweep). At 128 channels (512^2) the GEMM is epilogue-bound and the fused form measured SLOWER (+230 us per
+        # GEMM against a 100 us sweep), so those keep the two-sweep backward.
+        fuse = lambda t, st, n: (t, st, w[p + n + ".weight"], w[p + n + ".bias"]) if t.shape[-1] >= _GN_BWD_FUSE_MIN_C else None
+        dn2 = ops.conv3x3(dout, w[p + ".conv2.bwd"], gn_bwd=fuse(h1, st2, ".norm2"))
         dh1 = ops.groupnorm_bwd(h1, dn2, w[p + ".norm2.weight"], w[p + ".norm2.bias"], st2, silu=True, out=dn2)
-        dn1 = ops.conv3x3(dh1, w[p + ".conv1.bwd"])
+        dn1 = ops.conv3x3(dh1, w[p + ".conv1.bwd"], gn_bwd=fuse(x, st1, ".norm1"))
         add = dout
         if p + ".conv_shortcut.bwd" in w:
             N, H, W, C = dout.shape
@@ -245,7 +252,7 @@ class VAEEncoderB200:
                                      self._dyn.data_ptr(), st), "vae_grad_scale")
         ops._chk(L.gd_vae_sample_bwd_dyn(g.data_ptr(), mom.data_ptr(), noise.data_ptr(), dmom.data_ptr(), B, h * w_, 64,
                                          scaling, float(clip), float(scale), self._dyn.data_ptr(), st), "vae_sample_bwd")
-        dn = ops.conv3x3(dmom, self.w["conv_out.bwd"])
+        dn = ops.conv3x3(dmom, self.w["conv_out.bwd"], gn_bwd=(x_out, stn, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"]))
         d = ops.groupnorm_bwd(x_out, dn, self.w["encoder.conv_norm_out.weight"], self.w["encoder.conv_norm_out.bias"], stn, silu=True, out=dn)
         for rec in reversed(saved):
             if rec[0] == "resnet":

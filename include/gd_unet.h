@@ -77,6 +77,12 @@ typedef struct {
      the chosen kernel variant cannot produce them (split-K, ragged N, transposed / GEGLU epilogue): the output tensor is
      complete, the statistics are not written. */
   void* colstats;
+  /* optional GroupNorm(+SiLU)-BACKWARD producer epilogue for the data-gradient GEMM in front of that backward: gn_coef =
+     fp32 [images][N][4] from gd_unet_gn_bwd_coef, residual = the GroupNorm INPUT x (same layout as C; it is NOT added),
+     colstats required. C receives g = acc * silu'(GN(x)) and colstats sum g | sum g*xh per 32-row block and column, which
+     gd_unet_groupnorm_bwd_g turns into dx without a statistics sweep over x and dz. Returns GD_UNET_NO_COLSTATS when the
+     shape cannot take this epilogue: C then holds the PLAIN product (residual ignored), use gd_unet_groupnorm_bwd. */
+  const void* gn_coef;
 } GdGemmArgs;
 
 int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
@@ -206,6 +212,15 @@ int gd_vae_dimg(const void* dx, float* dcolor_nchw, int B, int H, int W, int Cp,
 int gd_unet_groupnorm_colstats(const void* x, void* y, const void* gamma, const void* beta, float* mean_rstd,
                                const float* statsA, int Ca, const float* statsB, int Cb, int N, int HW, int C,
                                int groups, float eps, int silu, gd_ustream_t stream);
+
+/* GroupNorm(+SiLU) backward split around the producing data-gradient GEMM (see GdGemmArgs.gn_coef):
+   gd_unet_gn_bwd_coef: stats = (mean, rstd) [N*groups][2] of the forward -> coef fp32 [N][C][4] = (ya, yb, ca, cb),
+     xh = x*ca + cb, y = x*ya + yb = xh*gamma + beta.
+   gd_unet_groupnorm_bwd_g: g = dz*silu'(y) (the GEMM output) and its colstats -> dx = rstd*(gamma*g - S1 - xh*S2) (+ add). */
+int gd_unet_gn_bwd_coef(const float* stats, const void* gamma, const void* beta, float* coef, int N, int C, int groups,
+                        gd_ustream_t stream);
+int gd_unet_groupnorm_bwd_g(const void* x, const void* g, const void* add, void* dx, const void* gamma, const void* beta,
+                            const float* stats, const float* colstats, int N, int HW, int C, int groups, gd_ustream_t stream);
 
 /* F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=False) on fp32 planes [BC, Hi, Wi] -> [BC, Ho, Wo]
    (stable_diffusion_guidance.py:387-396: the rendered batch is resized to 512^2 before encode_images), and its

@@ -179,6 +179,30 @@ def test_gemm_colstats_feed_groupnorm(ops, N, H, W, Cin, Cout):
     assert rel(out, out2) < 2e-4 and rel(stats, stats2) < 1e-4
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 128, 128, 128, 128), (2, 64, 64, 256, 256), (4, 64, 64, 512, 256), (1, 16, 16, 512, 512)])
+def test_gemm_groupnorm_backward_producer_epilogue(ops, N, H, W, Cin, Cout):
+    """Data-gradient conv whose epilogue multiplies by silu'(GN(x)) and emits sum g | sum g*xh (GdGemmArgs.gn_coef), followed by
+    groupnorm_bwd on those sums, against the unfused conv + two-sweep GroupNorm backward and against torch autograd. The last
+    shape is too small for the fused epilogue (split-K): the call must fall back and still be right."""
+    x = rnd(N, H, W, Cout)                                  # GroupNorm input (forward activation)
+    gam, bet = rnd(Cout), rnd(Cout)
+    dz_in, w = rnd(N, H, W, Cin, seed=5), rnd(Cout, 3, 3, Cin, scale=(9 * Cin) ** -0.5, seed=6)
+    add = rnd(N, H, W, Cout, seed=7)
+    _, stats = ops.groupnorm_stats(x, gam, bet, eps=1e-6, silu=True)
+    plain = ops.conv3x3(dz_in, w)
+    d_plain = ops.groupnorm_bwd(x, plain, gam, bet, stats, silu=True, add=add)
+    g = ops.conv3x3(dz_in, w, gn_bwd=(x, stats, gam, bet))
+    fused_taken = bool(getattr(g, "_gd_is_g", False))
+    assert fused_taken == (N * H * W >= 4096), "fused epilogue expected for the large shapes only"
+    d_fused = ops.groupnorm_bwd(x, g, gam, bet, stats, silu=True, add=add)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    z = F.silu(F.group_norm(xr, 32, gam.float(), bet.float(), 1e-6))
+    z.backward(plain.float().permute(0, 3, 1, 2))
+    ref = xr.grad.permute(0, 2, 3, 1) + add.float()
+    assert rel(d_plain, ref) < 2e-3
+    assert rel(d_fused, ref) < 2e-3 and rel(d_fused, d_plain) < 2e-3
+
+
 def test_time_embedding_and_small_ops(ops):
     t = torch.tensor([20.0, 500.0, 979.0, 980.0], device="cuda")
     e = ops.timestep_embedding(t, 320)
