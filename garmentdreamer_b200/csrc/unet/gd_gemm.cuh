@@ -56,7 +56,13 @@ struct GemmKParams {
                               // values this GEMM stores (GroupNorm statistics of the consumer without another pass over the tensor)
   const float4* gn_coef;      // MODE 4 (GroupNorm-backward producer): [images][N] (ya, yb, ca, cb); p.residual = the GroupNorm input x.
                               // The epilogue stores g = acc * silu'(x*ya + yb) and colstats = per 32-row block sum g | sum g*(x*ca + cb)
-  int a_halo;                 // CTA pairs, 3x3 conv on rows of >= 128 pixels: ONE haloed A tile (130 pixels x 64 ch) per (dy, channel
+  uint32_t halo_bytes;        // bytes of one haloed A slot (1024-aligned)
+  int patch_w_tiles, patch_tiles_per_img;   // a_halo == 2: 8-pixel x 16-row patches per image row of patches / per image
+  int a_halo;                 // 2 = images narrower than 128 pixels: an M tile is a PATCH of 8 pixels x 16 rows and the A slot holds
+                              // its (8+2) x 16 haloed pixels of image rows y0+dy .. (TMA box {64 ch, 10, 16, 1}); tap dx starts dx pixels
+                              // in, every image row of the patch is one 8-row UMMA group and the groups are 10 pixels (1280 B) apart
+                              // (descriptor SBO = 1280): A traffic / 2.4, and output rows map to pixels patch-wise. 1 =
+                              // CTA pairs, 3x3 conv on rows of >= 128 pixels: ONE haloed A tile (130 pixels x 64 ch) per (dy, channel
                               // block) serves the three dx taps through row-shifted UMMA descriptors (A traffic / 3)
 };
 
@@ -111,6 +117,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+constexpr uint32_t kPatchBytes = 16 * 10 * 128;   // a_halo == 2: 16 image rows x 10 pixels x 128 B
 constexpr uint32_t kHaloBytes = 17 * 1024;   // 130 rows x 128 B = 16640 B of haloed A, padded to the 1024-byte atom
 // Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, F16 x F16, K-major A and B.
 __device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
@@ -203,7 +213,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (bres && smem != smem_raw) __trap();   // resident mode is sized without the alignment slack (the base is 1 KB aligned)
   const uint32_t b_slot = (b_bytes + 1023) & ~1023u;
   const bool halo = TWO && p.a_halo;
-  const uint32_t stage_bytes = halo ? (bres ? kHaloBytes : kHaloBytes + 3 * b_slot) : (bres ? a_bytes : a_bytes + b_slot);   // resident B: the ring holds A only
+  const bool patch = TWO && p.a_halo == 2;
+  const uint32_t stage_bytes = halo ? (bres ? p.halo_bytes : p.halo_bytes + 3 * b_slot) : (bres ? a_bytes : a_bytes + b_slot);   // resident B: the ring holds A only
   uint8_t* b_res = smem + (size_t)S * stage_bytes;                      // [num_kb][b_slot] when resident
   uint8_t* stg_all = b_res + (bres ? (size_t)p.num_kb * b_slot : 0);    // epilogue staging: kEpiWarps x stg_bufs x 2 KB (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + (size_t)kEpiWarps * p.stg_bufs * 2048);
@@ -261,7 +272,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.mode_conv) {
           // tile = imgs_box images x rows_box rows x box_w pixels (box_w < img_w: part of one row)
           const int tiles_per_img = p.rows_per_image / kBM;
-          if (p.imgs_box == 1) {
+          if (patch) {
+            const int t_in = m_blk % p.patch_tiles_per_img;
+            a_c3 = m_blk / p.patch_tiles_per_img;
+            a_c2 = (t_in / p.patch_w_tiles) * 16;
+            a_c1 = (t_in % p.patch_w_tiles) * 8;
+          } else if (p.imgs_box == 1) {
             const int t_in = m_blk % tiles_per_img;
             a_c3 = m_blk / tiles_per_img;
             a_c2 = (t_in / p.tiles_per_row) * p.rows_box;
@@ -280,8 +296,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int s = it % S;
               bar_wait(&empty[s], ((it / S) & 1) ^ 1);
               uint8_t* sa = smem + (size_t)s * stage_bytes;
-              uint8_t* sb = sa + kHaloBytes;
-              if (rank == 0) bar_expect_tx(&full[s], 2u * (130u * 128u + (bres ? 0u : 3u * b_bytes)));
+              uint8_t* sb = sa + p.halo_bytes;
+              if (rank == 0) bar_expect_tx(&full[s], 2u * ((patch ? kPatchBytes : 130u * 128u) + (bres ? 0u : 3u * b_bytes)));
               tma_load_4d_2sm(sa, &tmA, &full[s], cb * kBK, a_c1 - 1, a_c2 + dyi - 1, a_c3);
               if (!bres) {
 #pragma unroll
@@ -341,14 +357,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t sa = s2u(smem + (size_t)s * stage_bytes);
             // weight tiles: behind the A tile in the stage, or (resident B) tap (dy, dx), channel block cb of the resident copy
             const int dyi = sbk / p.kb_per_tap, cbi = sbk % p.kb_per_tap;
-            const uint32_t sb = bres ? s2u(b_res) + (uint32_t)((dyi * 3) * p.kb_per_tap + cbi) * b_slot : sa + kHaloBytes;
+            const uint32_t sb = bres ? s2u(b_res) + (uint32_t)((dyi * 3) * p.kb_per_tap + cbi) * b_slot : sa + p.halo_bytes;
             const uint32_t sb_step = bres ? (uint32_t)p.kb_per_tap * b_slot : b_slot;
 #pragma unroll
             for (int dxi = 0; dxi < 3; dxi++) {
               // tap dx reads rows dx .. dx+127 of the 130-row tile: the descriptor simply starts dx rows (128 B each) later. The
               // unit derives the 128B-swizzle XOR from the absolute shared-memory address bits [7:9], exactly like the TMA that
               // wrote the tile, so no base_offset is set (measured: with base_offset = dx the result is wrong).
-              const uint64_t da = umma_desc_sw128(sa + (uint32_t)dxi * 128u), db = umma_desc_sw128(sb + (uint32_t)dxi * sb_step);
+              const uint64_t da = patch ? umma_desc_sw128_sbo(sa + (uint32_t)dxi * 128u, 1280u) : umma_desc_sw128(sa + (uint32_t)dxi * 128u);
+              const uint64_t db = umma_desc_sw128(sb + (uint32_t)dxi * sb_step);
 #pragma unroll
               for (int k = 0; k < kBK / 16; k++)
                 umma_f16_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (sbk | dxi | k) ? 1u : 0u);
@@ -408,7 +425,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = TWO ? 2 * ((tt / n_tiles) % m_tiles) + (int)rank : (tt / n_tiles) % m_tiles;
       const int zh = z % p.heads, zb = z / p.heads;
       const int acc = lt & 1;
-      const int row = m_blk * kBM + q * 32 + lane;
+      // global output row of tile row r: linear, or (patch tiles) pixel (y0 + r/8, x0 + r%8) of the tile's image
+      int prow0 = m_blk * kBM, pstep = 8;
+      if (patch) {
+        const int t_in = m_blk % p.patch_tiles_per_img;
+        prow0 = (m_blk / p.patch_tiles_per_img) * p.rows_per_image + (t_in / p.patch_w_tiles) * 16 * p.img_w + (t_in % p.patch_w_tiles) * 8;
+        pstep = p.img_w;
+      }
+      auto grow = [&](int r) { return prow0 + (r >> 3) * pstep + (r & 7); };
+      const int row = grow(q * 32 + lane);
       const bool row_ok = row < p.M;
       const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;
       const int img = p.rows_per_image > 0 ? (m_blk * kBM + q * 32) / p.rows_per_image : 0;  // uniform per warp
@@ -578,8 +603,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int it = 0; it < 4; it++) {
                 const int r = it * 8 + (lane >> 2);
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
-                if (row0 + r < p.M) {
-                  *reinterpret_cast<uint4*>(p.C + coff + (long long)(row0 + r) * p.ldc + n0 + piece * 8) = val;
+                const int orow = grow(q * 32 + r);
+                if (orow < p.M) {
+                  *reinterpret_cast<uint4*>(p.C + coff + (long long)orow * p.ldc + n0 + piece * 8) = val;
                   if constexpr (gnb) {   // sum g | sum g * xh (the GroupNorm backward's two reductions)
                     const uint4 valx = *reinterpret_cast<const uint4*>(stg + 2048 + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
                     const __half2* hv = reinterpret_cast<const __half2*>(&val);

@@ -805,11 +805,21 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   static const bool halo_enabled = []() { const char* e = getenv("GD_GEMM_HALO"); return !(e && e[0] == '0'); }();
   bool a_halo = halo_enabled && two && a->ntaps == 9 && a->a_box[1] == gdu::kBM && a->a_box[2] == 1 && a->a_box[3] == 1 && a->Ck % gdu::kBK == 0;
   for (int t = 0; a_halo && t < 9; t++) a_halo = a->tap_dx[t] == t % 3 - 1 && a->tap_dy[t] == t / 3 - 1 && a->tap_c[t] == 0;
+  // images narrower than 128 pixels: M tiles become 8 x 16 pixel patches with a haloed A slot per (dy, channel block), see
+  // GemmKParams.a_halo == 2. GD_GEMM_PATCH=0 switches it off (A/B timing).
+  static const bool patch_enabled = []() { const char* e = getenv("GD_GEMM_PATCH"); return !(e && e[0] == '0'); }();
+  static const bool tma_store_env = []() { const char* e = getenv("GD_GEMM_TMA_STORE"); return e && e[0] == '1'; }();
+  bool a_patch = patch_enabled && !tma_store_env && !a_halo && two && a->ntaps == 9 && a->a_box[1] < gdu::kBM && a->a_box[3] == 1 &&
+                 a->img_w % 8 == 0 && a->img_h % 16 == 0 && a->Ck % gdu::kBK == 0 && !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED));
+  for (int t = 0; a_patch && t < 9; t++) a_patch = a->tap_dx[t] == t % 3 - 1 && a->tap_dy[t] == t / 3 - 1 && a->tap_c[t] == 0;
+  const size_t halo_bytes = a_patch ? (size_t)gdu::kPatchBytes : (size_t)gdu::kHaloBytes;
+  if (a_patch) a_halo = true;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->a_dim[0], (cuuint64_t)a->a_dim[1], (cuuint64_t)a->a_dim[2], (cuuint64_t)a->a_dim[3]};
     cuuint64_t str[3] = {(cuuint64_t)a->a_stride[0], (cuuint64_t)a->a_stride[1], (cuuint64_t)a->a_stride[2]};
     cuuint32_t box[4] = {(cuuint32_t)a->a_box[0], (cuuint32_t)(a->a_box[1] + (a_halo ? 2 : 0)), (cuuint32_t)a->a_box[2], (cuuint32_t)a->a_box[3]};
+    if (a_patch) { box[1] = 10; box[2] = 16; box[3] = 1; }
     const int rc = make_map(&tmA, a->A, 4, dims, str, box);
     if (rc != GD_UNET_OK) return rc;
   }
@@ -844,8 +854,11 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
   const size_t b_slot_bytes = (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
-  const size_t stage_bytes = a_halo ? (size_t)gdu::kHaloBytes + 3 * b_slot_bytes : (size_t)gdu::kBM * gdu::kBK * 2 + b_slot_bytes;
-  p.a_halo = a_halo ? 1 : 0;
+  const size_t stage_bytes = a_halo ? halo_bytes + 3 * b_slot_bytes : (size_t)gdu::kBM * gdu::kBK * 2 + b_slot_bytes;
+  p.a_halo = a_patch ? 2 : a_halo ? 1 : 0;
+  p.halo_bytes = (uint32_t)halo_bytes;
+  p.patch_w_tiles = a_patch ? a->img_w / 8 : 1;
+  p.patch_tiles_per_img = a_patch ? (a->img_w / 8) * (a->img_h / 16) : 1;
   // one persistent CTA per SM owns the shared memory: operand ring + epilogue staging + barriers/bias
   const int bias_stride = 32 * ((((BN + 31) / 32) + 1) / 2);   // bias floats per epilogue warp
   p.bias_stride = bias_stride;
@@ -878,7 +891,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   const bool bres_enabled = bres_env >= 0 ? bres_env == 1 : a_halo;
   p.b_resident = 0;
   if (bres_enabled && two && n_tiles_all == 1 && a->batch == 1 && a->heads == 1) {
-    const size_t a_bytes = a_halo ? (size_t)gdu::kHaloBytes : (size_t)gdu::kBM * gdu::kBK * 2;
+    const size_t a_bytes = a_halo ? halo_bytes : (size_t)gdu::kBM * gdu::kBK * 2;
     const size_t b_slot = (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
     const size_t res = (size_t)num_kb_all * b_slot, stg = (size_t)gdu::kEpiWarps * stg_bufs * 2048;
     if (res + stg + fixed_noslack + 3 * a_bytes <= smem_max && (size_t)m_tiles_all * a->batch >= 4 * 148) {
@@ -906,7 +919,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   }
   p.total_tiles = p.m_tiles * p.n_tiles * a->batch * p.ksplit;
   const size_t smem = p.b_resident
-                          ? (size_t)stages * (a_halo ? (size_t)gdu::kHaloBytes : (size_t)gdu::kBM * gdu::kBK * 2) + (size_t)num_kb_all * (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023) +
+                          ? (size_t)stages * (a_halo ? halo_bytes : (size_t)gdu::kBM * gdu::kBK * 2) + (size_t)num_kb_all * (((size_t)(BN / 2) * gdu::kBK * 2 + 1023) & ~(size_t)1023) +
                                 (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed_noslack
                           : stages * stage_bytes + (size_t)gdu::kEpiWarps * stg_bufs * 2048 + fixed;
   // output tensor map for the staged epilogue: [batch][head][M][N], 32 x 32 box, 64B swizzle

@@ -72,8 +72,10 @@ typedef struct {
   unsigned flags;
   int block_n;            /* 16..256, multiple of 16; 0 = choose */
   long long row_bias_ld;  /* row stride of row_bias in elements; 0 = N */
-  /* optional fused GroupNorm statistics of the OUTPUT (plain epilogue only): fp32 [ceil(M/32)][2][N], per 32-row block
-     and column the sum and the sum of squares of the fp16 values stored. gd_unet_gemm returns GD_UNET_NO_COLSTATS (1) when
+  /* optional fused GroupNorm statistics of the OUTPUT (plain epilogue only): fp32 [ceil(M/32)][2][N], per block of 32 output
+     rows and column the sum and the sum of squares of the fp16 values stored. The blocks partition the rows of each image
+     (rows_per_image % 32 == 0) in tile order -- 32 consecutive rows, or four 8-pixel row segments of a patch tile -- so only
+     sums over whole images are defined; that is what gd_unet_groupnorm_colstats consumes. gd_unet_gemm returns GD_UNET_NO_COLSTATS (1) when
      the chosen kernel variant cannot produce them (split-K, ragged N, transposed / GEGLU epilogue): the output tensor is
      complete, the statistics are not written. */
   void* colstats;
