@@ -588,6 +588,40 @@ k_conv_in(const __half* __restrict__ x, const __half* __restrict__ w, const __ha
     *reinterpret_cast<uint4*>(yp + co) = *reinterpret_cast<const uint4*>(o);
   }
 }
+// conv_in on the tensor cores: im2col rows A[(n,y,x)][(ky*3+kx)*4 + c] (36 of 64 columns, the rest zero) from the fp16 NCHW
+// latents; the 3x3x4 -> Cout convolution is then one K = 64 GEMM (k_gemm_tcgen05) whose epilogue also leaves the GroupNorm
+// statistics of the first resnet. One thread per (pixel, 16-byte chunk of its 128-byte row).
+__global__ void __launch_bounds__(256)
+k_unet_im2col4(const __half* __restrict__ x, __half* __restrict__ A, int N, int H, int W) {
+  pdl_entry();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W, i = t >> 3;
+  const int u = (int)(t & 7);
+  if (i >= (long long)N * HW) return;
+  const int px = (int)(i % W), py = (int)((i / W) % H), n = (int)(i / HW);
+  __align__(16) __half v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = u * 8 + j, tap = k >> 2, c = k & 3;
+    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+    const bool ok = k < 36 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+    v[j] = ok ? x[((long long)n * 4 + c) * HW + (long long)yy * W + xx] : __float2half_rn(0.f);
+  }
+  reinterpret_cast<uint4*>(A)[t] = *reinterpret_cast<const uint4*>(v);
+}
+// conv_out tail: the first 4 of `ld` fp16 channels per pixel (NHWC) -> NCHW fp32
+__global__ void __launch_bounds__(256)
+k_unpack4_nchw(const __half* __restrict__ x, float* __restrict__ y, int N, long long HW, int ld) {
+  pdl_entry();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * HW) return;
+  const long long n = i / HW, p = i % HW;
+  const uint2 v = *reinterpret_cast<const uint2*>(x + i * ld);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  float* yo = y + n * 4 * HW + p;
+  yo[0] = a.x; yo[HW] = a.y; yo[2 * HW] = b.x; yo[3 * HW] = b.y;
+}
 // conv_out: Cout = 4, NHWC fp16 in -> NCHW fp32 out. One warp per pixel.
 __global__ void __launch_bounds__(256)
 k_conv_out(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
@@ -1029,7 +1063,8 @@ int gd_unet_flash_attn_ex(const void* q, const void* k, const void* vt, void* ou
   // long key ranges (self-attention of the 64^2 / 32^2 / 16^2 latent layers): single-pass kernel, two Q tiles per CTA.
   // GD_ATTN_TWO_PASS=1 keeps the two-pass kernel for A/B timing.
   static const bool two_pass_only = []() { const char* e = getenv("GD_ATTN_TWO_PASS"); return e && e[0] == '1'; }();
-  if (!two_pass_only && p.n_kv >= 2) {
+  static const int attn2_min_kv = []() { const char* e = getenv("GD_ATTN2_MIN_KV"); return e ? atoi(e) : 1; }();
+  if (!two_pass_only && p.n_kv >= attn2_min_kv && Tq >= 128) {
     const size_t smem2 = 2 * gdu::kQBytes + gdu::kAttn2Stages * (gdu::kKBytes + gdu::kVBytes) + 1024 + 512;
     launch_pdl(gdu::k_flash_attn2, dim3((Tq + 255) / 256, B * heads), dim3(gdu::kAttn2Threads), smem2, stream, tmQ, tmK, tmV, p);
     LAUNCH_CHECK("k_flash_attn2");
@@ -1138,6 +1173,20 @@ int gd_unet_conv_in(const void* x, const void* w, const void* bias, void* y, int
   launch_pdl(gdu::k_conv_in, dim3((unsigned)((pix + 127) / 128)), dim3(128), (size_t)((size_t)Cout * 37 * 2), (cudaStream_t)((cudaStream_t)s), 
       (const __half*)x, (const __half*)w, (const __half*)bias, (__half*)y, N, H, W, Cout);
   LAUNCH_CHECK("k_conv_in");
+  return GD_UNET_OK;
+}
+int gd_unet_im2col4(const void* x, void* A, int N, int H, int W, gd_ustream_t s) {
+  if (!x || !A || N < 1 || H < 1 || W < 1) return fail(GD_UNET_ERR_INVALID_ARG, "im2col4: bad argument");
+  const long long t = (long long)N * H * W * 8;
+  launch_pdl(gdu::k_unet_im2col4, dim3((unsigned)((t + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)x, (__half*)A, N, H, W);
+  LAUNCH_CHECK("k_unet_im2col4");
+  return GD_UNET_OK;
+}
+int gd_unet_unpack4_nchw(const void* x, float* y, int N, long long HW, int ld, gd_ustream_t s) {
+  if (!x || !y || N < 1 || HW < 1 || ld < 4 || ld % 4) return fail(GD_UNET_ERR_INVALID_ARG, "unpack4_nchw: ld must be a multiple of 4");
+  const long long t = (long long)N * HW;
+  launch_pdl(gdu::k_unpack4_nchw, dim3((unsigned)((t + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)s, (const __half*)x, y, N, HW, ld);
+  LAUNCH_CHECK("k_unpack4_nchw");
   return GD_UNET_OK;
 }
 int gd_unet_conv_out(const void* x, const void* w, const void* bias, float* y, int N, int H, int W, int Cin, gd_ustream_t s) {

@@ -58,6 +58,14 @@ class UNetB200:
             c = self.w[nme + ".to_k.weight"].shape[0]
             self._kv_off[nme] = (off, c)
             off += c
+        wi = self.w["conv_in.weight"]                                   # [320,3,3,4] -> im2col layout [320,64]
+        self._conv_in_w64 = torch.zeros((wi.shape[0], 64), dtype=torch.float16, device=wi.device)
+        self._conv_in_w64[:, :36] = wi.reshape(wi.shape[0], 36)
+        wo = self.w["conv_out.weight"]                                  # [4,3,3,320] -> Cout padded to 16
+        self._conv_out_w16 = torch.zeros((16,) + tuple(wo.shape[1:]), dtype=torch.float16, device=wo.device)
+        self._conv_out_w16[:4] = wo
+        self._conv_out_b16 = torch.zeros(16, dtype=torch.float16, device=wo.device)
+        self._conv_out_b16[:4] = self.w["conv_out.bias"]
         self._ctx_wk = torch.cat([self.w[nme + ".to_k.weight"] for nme in names]).contiguous()
         self._ctx_wv = torch.cat([self.w[nme + ".to_v.weight"] for nme in names]).contiguous()
         self._ctx_kv = None
@@ -150,14 +158,21 @@ class UNetB200:
     # ---- forward -------------------------------------------------------------------------------
     def _forward_impl(self, sample, t_f32, ctx):
         w = self.w
-        x = ops.conv_in(sample, w["conv_in.weight"], w["conv_in.bias"])
+        N_, _, H_, W_ = sample.shape
+        if H_ % 16 == 0 and W_ % 8 == 0:   # conv_in / conv_out on the tensor-core GEMM (im2col rows / Cout padded to 16)
+            x = ops.linear(ops.im2col4(sample), self._conv_in_w64, w["conv_in.bias"], want_stats=True)
+            x = ops.carry_stats(x, x.view(N_, H_, W_, -1))
+        else:
+            x = ops.conv_in(sample, w["conv_in.weight"], w["conv_in.bias"])
         if self._trace is not None:
             self._trace("in", "conv_in", sample, x)
         temb = ops.timestep_embedding(t_f32, 320)
         emb = ops.small_linear(temb, w["time_embedding.linear_1.weight"], w["time_embedding.linear_1.bias"], silu_out=True)
         # every consumer (ResnetBlock2D.time_emb_proj) applies SiLU first: do it once here
         emb = ops.small_linear(emb, w["time_embedding.linear_2.weight"], w["time_embedding.linear_2.bias"], silu_out=True)
-        emb = ops.small_linear(emb, self._temb_w, self._temb_b)   # every time_emb_proj at once
+        # every time_emb_proj at once: [B, 1280] x [20160, 1280]^T. On the tensor-core GEMM (one M tile; 52 MB of weights stream
+        # once at HBM speed, ~12 us) -- the per-output-warp GEMV kernel was instruction-bound here (75 us).
+        emb = ops.linear(emb, self._temb_w, self._temb_b)
         Tk = ctx.shape[1]
         self._ctx_kv = (ops.linear(ctx, self._ctx_wk), ops.linear_transposed(ctx, self._ctx_wv, (Tk + 7) // 8 * 8))
         skips = [x]
@@ -190,7 +205,10 @@ class UNetB200:
                     self._trace("up", p, x_in, x)
         x_in = x
         x = ops.groupnorm(x, w["conv_norm_out.weight"], w["conv_norm_out.bias"], eps=1e-5, silu=True)
-        out = ops.conv_out(x, w["conv_out.weight"], w["conv_out.bias"])  # NCHW fp32 (fp16-rounded)
+        if H_ % 16 == 0 and W_ % 8 == 0:
+            out = ops.unpack4_nchw(ops.conv3x3(x, self._conv_out_w16, self._conv_out_b16))   # NCHW fp32 (fp16-rounded)
+        else:
+            out = ops.conv_out(x, w["conv_out.weight"], w["conv_out.bias"])  # NCHW fp32 (fp16-rounded)
         if self._trace is not None:
             self._trace("out", "conv_out", x_in, out)
         return out

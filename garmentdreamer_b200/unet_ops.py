@@ -100,6 +100,9 @@ def lib():
         L.gd_unet_init.restype = ctypes.c_int
         L.gd_unet_groupnorm_colstats.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, f, i, vp]
         L.gd_unet_groupnorm_colstats.restype = ctypes.c_int
+        L.gd_unet_im2col4.argtypes = [vp, vp, i, i, i, vp]
+        L.gd_unet_unpack4_nchw.argtypes = [vp, vp, i, ctypes.c_longlong, i, vp]
+        L.gd_unet_im2col4.restype = L.gd_unet_unpack4_nchw.restype = ctypes.c_int
         L.gd_unet_gn_bwd_coef.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.gd_unet_groupnorm_bwd_g.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
         L.gd_unet_gn_bwd_coef.restype = L.gd_unet_groupnorm_bwd_g.restype = ctypes.c_int
@@ -520,6 +523,22 @@ def conv_out(x, w, bias):
     out = torch.empty((N, 4, H, W), dtype=torch.float32, device=x.device)
     _chk(lib().gd_unet_conv_out(_h(x).data_ptr(), _h(w).data_ptr(), bias.data_ptr(), out.data_ptr(), N, H, W, Cin,
                                 _stream()), "conv_out")
+    return out
+
+
+def im2col4(x_nchw):
+    """[N,4,H,W] fp16 latents -> [N*H*W, 64] im2col rows of the 3x3 conv_in (columns (ky*3+kx)*4 + c, 36..63 zero)."""
+    N, _, H, W = x_nchw.shape
+    out = torch.empty((N * H * W, 64), dtype=torch.float16, device=x_nchw.device)
+    _chk(lib().gd_unet_im2col4(_h(x_nchw).data_ptr(), out.data_ptr(), N, H, W, _stream()), "im2col4")
+    return out
+
+
+def unpack4_nchw(x):
+    """[N,H,W,C>=4] fp16 NHWC -> [N,4,H,W] fp32 (first four channels)."""
+    N, H, W, C = x.shape
+    out = torch.empty((N, 4, H, W), dtype=torch.float32, device=x.device)
+    _chk(lib().gd_unet_unpack4_nchw(_h(x).data_ptr(), out.data_ptr(), N, H * W, C, _stream()), "unpack4_nchw")
     return out
 
 

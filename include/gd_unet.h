@@ -215,6 +215,13 @@ int gd_unet_groupnorm_colstats(const void* x, void* y, const void* gamma, const 
                                const float* statsA, int Ca, const float* statsB, int Cb, int N, int HW, int C,
                                int groups, float eps, int silu, gd_ustream_t stream);
 
+/* conv_in / conv_out of the UNet (4 latent channels) on the tensor-core GEMM:
+   gd_unet_im2col4: x fp16 NCHW [N,4,H,W] -> A fp16 [N*H*W][64], A[p][(ky*3+kx)*4 + c] = x[n, c, y+ky-1, x+kx-1] (zero outside the
+     image and in columns 36..63); conv_in is then gd_unet_gemm with the weights laid out [Cout][64] the same way.
+   gd_unet_unpack4_nchw: the first 4 of ld fp16 channels per pixel (the 3x3 conv_out run with Cout padded to 16) -> fp32 NCHW. */
+int gd_unet_im2col4(const void* x_nchw, void* A, int N, int H, int W, gd_ustream_t stream);
+int gd_unet_unpack4_nchw(const void* x_nhwc, float* y_nchw, int N, long long HW, int ld, gd_ustream_t stream);
+
 /* GroupNorm(+SiLU) backward split around the producing data-gradient GEMM (see GdGemmArgs.gn_coef):
    gd_unet_gn_bwd_coef: stats = (mean, rstd) [N*groups][2] of the forward -> coef fp32 [N][C][4] = (ya, yb, ca, cb),
      xh = x*ca + cb, y = x*ya + yb = xh*gamma + beta.

@@ -15,13 +15,14 @@ def timeit(fn, iters=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
 
-for B, T, heads in [(8, 4096, 5), (8, 1024, 10), (8, 256, 20), (8, 64, 20)]:
+for B, T, heads, Tk in [(8, 4096, 5, 4096), (8, 1024, 10, 1024), (8, 256, 20, 256), (8, 64, 20, 64), (8, 4096, 5, 77), (8, 1024, 10, 77), (8, 256, 20, 77)]:
     C = heads * 64
     g = torch.Generator(device="cuda").manual_seed(0)
     q = torch.randn(B, T, C, generator=g, device="cuda").half()
-    k = torch.randn(B, T, C, generator=g, device="cuda").half()
-    vt = torch.randn(B, C, T, generator=g, device="cuda").half()
+    k = torch.randn(B, Tk, C, generator=g, device="cuda").half()
+    vt = torch.zeros(B, C, (Tk + 7) // 8 * 8, device="cuda").half()
+    vt[:, :, :Tk] = torch.randn(B, C, Tk, generator=g, device="cuda").half()
     o = torch.empty(B, T, C, dtype=torch.float16, device="cuda")
-    us = timeit(lambda: ops.flash_attention(q, k, vt, heads, T, 0.125, out=o))
-    flops = 4.0 * B * heads * T * T * 64
-    print(f"attn B={B} T={T} heads={heads}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s")
+    us = timeit(lambda: ops.flash_attention(q, k, vt, heads, Tk, 0.125, out=o))
+    flops = 4.0 * B * heads * T * Tk * 64
+    print(f"attn B={B} T={T} Tk={Tk} heads={heads}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s")
