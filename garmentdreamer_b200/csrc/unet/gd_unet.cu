@@ -1388,11 +1388,14 @@ int gd_unet_groupnorm_bwd(const void* x, const void* dz, const void* add, void* 
   float2* bstats = device_scratch()->gn_bstats;
   const int splits = gn_big_splits(N, HW, C);
   if ((size_t)N * groups * splits > kGnBig) return fail(GD_UNET_ERR_INVALID_ARG, "groupnorm_bwd: N * groups * splits exceeds the scratch");
-  if (256 % (C / 8) == 0) {   // register-resident coefficients, software-pipelined loads
-    if (silu) launch_pdl(gdu::k_gn_bwd_stats_fast<true, 2>, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
-                         (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits);
-    else launch_pdl(gdu::k_gn_bwd_stats_fast<false, 2>, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
-                    (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits);
+  if (256 % (C / 8) == 0) {   // register-resident coefficients, software-pipelined loads. GD_GN_BWD_STATS_PIPE=0: 8 plain loads in
+    // flight per thread instead (measured slower: VAE backward 7.48 vs 7.37 ms)
+    static const bool pipe = []() { const char* e = getenv("GD_GN_BWD_STATS_PIPE"); return !(e && e[0] == '0'); }();
+#define GD_BS(S_, U_, P_) launch_pdl(gdu::k_gn_bwd_stats_fast<S_, U_, P_>, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, \
+    (const __half*)dz, (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits)
+    if (pipe) { if (silu) GD_BS(true, 2, true); else GD_BS(false, 2, true); }
+    else { if (silu) GD_BS(true, 4, false); else GD_BS(false, 4, false); }
+#undef GD_BS
   } else {
     launch_pdl(gdu::k_gn_bwd_stats, dim3(N, splits), dim3(256), (size_t)0, s, (const __half*)x, (const __half*)dz,
                (const float2*)stats, (const __half*)gamma, (const __half*)beta, part, HW, C, groups, splits, silu);

@@ -131,7 +131,7 @@ k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dz, cons
 // Pass 1, fast flavour (C/8 divides 256: the VAE's 128 / 256 / 512 channels): a thread owns ONE 8-channel chunk for the
 // whole sweep -- coefficients in registers (xh = x*ca + cb, y = x*ya + yb), no index arithmetic -- with the 16-byte loads of
 // the next U pixels in flight during the math. Same partial layout as k_gn_bwd_stats.
-template <bool SILU, int U>
+template <bool SILU, int U, bool PIPE>
 __global__ void __launch_bounds__(256)
 k_gn_bwd_stats_fast(const __half* __restrict__ x, const __half* __restrict__ dz, const float2* __restrict__ stats,
                     const __half* __restrict__ gamma, const __half* __restrict__ beta, float2* __restrict__ part,
@@ -155,21 +155,27 @@ k_gn_bwd_stats_fast(const __half* __restrict__ x, const __half* __restrict__ dz,
   const size_t base = (size_t)n * HW * C;
   const uint4* xb = reinterpret_cast<const uint4*>(x + base) + ch;
   const uint4* gb = reinterpret_cast<const uint4*>(dz + base) + ch;
-  uint4 xv[U], gv[U], nxv[U], ngv[U];
-  auto fetch = [&](int pp, uint4 (&X)[U], uint4 (&G)[U]) {
+  // PIPE: the loads of the next U pixels are in flight during the math (2 x 2U x 16 B per thread held in registers);
+  // !PIPE: 2U loads issued together, the other resident CTAs cover the math phase.
+  uint4 xv[U], gv[U], nxv[PIPE ? U : 1], ngv[PIPE ? U : 1];
+  auto fetch = [&](int pp, uint4* X, uint4* G) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const bool ok = pp + u * PP < p1;
       const size_t o = (size_t)(pp + u * PP) * C8;
-      X[u] = ok ? xb[o] : make_uint4(0, 0, 0, 0);
-      G[u] = ok ? gb[o] : make_uint4(0, 0, 0, 0);   // zero gradient: padding pixels add nothing
+      X[u] = ok ? __ldg(xb + o) : make_uint4(0, 0, 0, 0);
+      G[u] = ok ? __ldg(gb + o) : make_uint4(0, 0, 0, 0);   // zero gradient: padding pixels add nothing
     }
   };
-  fetch(p0 + pl, nxv, ngv);
+  if (PIPE) fetch(p0 + pl, nxv, ngv);
   for (int pix = p0 + pl; pix < p1; pix += PP * U) {
+    if (PIPE) {
 #pragma unroll
-    for (int u = 0; u < U; u++) { xv[u] = nxv[u]; gv[u] = ngv[u]; }
-    fetch(pix + PP * U, nxv, ngv);
+      for (int u = 0; u < U; u++) { xv[u] = nxv[u]; gv[u] = ngv[u]; }
+      fetch(pix + PP * U, nxv, ngv);
+    } else {
+      fetch(pix, xv, gv);
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const __half2* xh2 = reinterpret_cast<const __half2*>(&xv[u]);
