@@ -296,6 +296,14 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 // The running maximum is LAZY: m only moves when the tile maximum exceeds it by more than 2^8 (P stays below 256, exact
 // in fp16's range; l and O are fp32), and only then O_q is rescaled in TMEM by the owning threads (tcgen05.ld/st of the
 // row) -- after the first tiles this almost never happens. TMEM: S0 S1 | O0 O1 | P0 P1 = 2x128 + 2x64 + 2x64 = 512 columns.
+//
+// Measured on B200 (clock64 timeline of one CTA, 64x64 latents, 2780 cycles per pair of 128x128 score tiles): per warp and
+// tile ~80 wait for S, ~130 tcgen05.ld, ~330 row maximum, ~1900 ex2 phase, ~150 wait for the previous P V, ~60 tcgen05.st.
+// Two bounds sit close together: the SFU (2 x 128 x 128 ex2 at 16 / clk / SM = 2048 cycles; halving the ex2 count halves the
+// ex2 phase) and the S -> softmax -> P -> P V barrier chain (~2400 cycles: with half the ex2 work the warps wait for S
+// instead). Variants tried and dropped because they did not move the total: a quarter of the ex2 on the FMA pipe
+// (Cody-Waite polynomial; +9 instructions per score made the warps issue-bound: 2980 cycles), and sixteen softmax warps
+// with two threads per row (same 2800 cycles).
 constexpr int kAttn2Threads = 64 + 8 * 32;
 constexpr int kAttn2Stages = 3;
 
