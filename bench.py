@@ -405,8 +405,9 @@ def main():
     achieved = abytes / (bwd_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_render_bwd + k_bwd_epilogue (raster backward)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": 203.0e6 if (P, B, S) == (100000, 4, 512) else None,
-                "traffic_source": "profiles/r02_raster_ncu_summary.txt (dram read+write of k_render_bwd + k_bwd_epilogue, c2)",
+                "traffic": 175.3e6 if (P, B, S) == (100000, 4, 512) else None,
+                "traffic_source": "profiles/r02_final_raster_ncu_summary.txt (dram read+write of k_render_bwd 73.0+21.8 MB + k_bwd_epilogue 76.7+3.8 MB, c2)",
+                "limiter": "instruction issue (ncu: 71 % of the issue slots, 353 M warp instructions; DRAM 2.4 % busy) -- the HBM roofline is the contract's yardstick",
                 "peak_source": peak_kind, "algorithmic_bytes": abytes, "launch_ms": bwd_ms, "R": R_total}
     if sds_roofline is not None:
         sds_roofline["raster_bwd"] = roofline

@@ -148,7 +148,7 @@ def dominant_gemm_probe(dev, peaks):
     each are captured in a CUDA graph; burst peak = a kernel timed alone."""
     out = []
     peak = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained"))
-    for name, (N_, H, W, Ci, Co), traffic in (("k_gemm_tcgen05<0,1> conv 128->128 @4x512^2 (VAE)", (4, 512, 512, 128, 128), 507.5e6),
+    for name, (N_, H, W, Ci, Co), traffic in (("k_gemm_tcgen05<0,1> conv 128->128 @4x512^2 (VAE)", (4, 512, 512, 128, 128), 502.0e6),
                                               ("k_gemm_tcgen05<0,1> conv 1280->1280 @8x16^2 (UNet)", (8, 16, 16, 1280, 1280), None)):
         x = torch.randn(N_, H, W, Ci, device=dev).half()
         w = (torch.randn(Co, 9 * Ci, device=dev) * (9 * Ci) ** -0.5).half()
@@ -174,7 +174,7 @@ def dominant_gemm_probe(dev, peaks):
         out.append({"kernel": name, "bound": "tensor", "launch_us": us, "algorithmic_flops": flops, "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic,   # dram read+write bytes per launch from the committed ncu --set full capture, or None
-                    "traffic_source": "profiles/r01_s7_gemm_conv128_512sq_details.txt" if traffic else None})
+                    "traffic_source": "profiles/r02_final_gemm_halo128_summary.txt (dram 268.8 MB read + 233.2 MB written; algorithmic 537 MB)" if traffic else None})
         del g
     return out
 
