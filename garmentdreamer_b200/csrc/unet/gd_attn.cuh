@@ -303,7 +303,8 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 // ex2 phase) and the S -> softmax -> P -> P V barrier chain (~2400 cycles: with half the ex2 work the warps wait for S
 // instead). Variants tried and dropped because they did not move the total: a quarter of the ex2 on the FMA pipe
 // (Cody-Waite polynomial; +9 instructions per score made the warps issue-bound: 2980 cycles), and sixteen softmax warps
-// with two threads per row (same 2800 cycles).
+// with two threads per row (same 2800 cycles); ex2.approx.f16x2 on packed exponents (ptxas emits TWO scalar MUFU.EX2.F16 per
+// pair, no packed SFU op on sm_100a: 255 -> 317 us).
 constexpr int kAttn2Threads = 64 + 8 * 32;
 constexpr int kAttn2Stages = 3;
 
