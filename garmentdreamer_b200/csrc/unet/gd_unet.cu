@@ -392,6 +392,49 @@ k_layernorm(const __half* __restrict__ x, __half* __restrict__ y, const __half* 
   pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
+  if ((C & 7) == 0 && C <= 1280) {
+    // the row lives in registers between the two passes: up to five 16-byte loads per lane, all issued before the first use
+    const int n8 = C >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
+    uint4 v[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) v[k] = (lane + 32 * k < n8) ? xr[lane + 32 * k] : make_uint4(0, 0, 0, 0);
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const float2 f = __half22float2(h[t]);
+        s += f.x + f.y; ss += f.x * f.x + f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
+    const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+    const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+    const uint4* b4 = reinterpret_cast<const uint4*>(beta);
+    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * C);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int c8 = lane + 32 * k;
+      if (c8 < n8) {
+        const uint4 gv = g4[c8], bv = b4[c8];
+        const __half2* h = reinterpret_cast<const __half2*>(&v[k]);
+        const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const float2 f = __half22float2(h[t]), ga = __half22float2(gh[t]), be = __half22float2(bh[t]);
+          oh[t] = __floats2half2_rn((f.x - mean) * rstd * ga.x + be.x, (f.y - mean) * rstd * ga.y + be.y);
+        }
+        yr[c8] = o;
+      }
+    }
+    return;
+  }
   const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)row * C);
   __half2* yr = reinterpret_cast<__half2*>(y + (size_t)row * C);
   float s = 0.f, ss = 0.f;
