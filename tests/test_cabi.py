@@ -44,3 +44,33 @@ def test_raster_host_side_validation():
     assert lib.gd_raster_forward(ctypes.byref(a), None) == -1  # neither shs nor colors
     assert b"exactly one" in lib.gd_last_error()
     assert lib.gd_launch_count() == 0
+
+
+def test_ctypes_mirrors_match_the_c_headers(tmp_path):
+    """Every struct of include/*.h has a ctypes mirror on the Python side of the boundary: compile the headers as C (gcc) and
+    compare sizeof and the offset of every field, so an argument added on one side only cannot go unnoticed."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    from garmentdreamer_b200 import _lib
+    from garmentdreamer_b200.parallel import GdPeerTable
+    from garmentdreamer_b200.unet_ops import GdGemmArgs
+    mirrors = {"GdView": _lib.GdView, "GdCounters": _lib.GdCounters, "GdFwdArgs": _lib.GdFwdArgs, "GdBwdArgs": _lib.GdBwdArgs,
+               "GdStateView": _lib.GdStateView, "GdPeerTable": GdPeerTable, "GdGemmArgs": GdGemmArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gd_raster.h"', '#include "gd_unet.h"', "int main(void) {"]
+    for name, cls in mirrors.items():
+        lines.append(f'  printf("{name} sizeof %zu\\n", sizeof({name}));')
+        for field in cls._fields_:
+            lines.append(f'  printf("{name} {field[0]} %zu\\n", offsetof({name}, {field[0]}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-x", "c", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    for line in out.strip().splitlines():
+        name, what, value = line.split()
+        cls = mirrors[name]
+        mine = ctypes.sizeof(cls) if what == "sizeof" else getattr(cls, what).offset
+        assert mine == int(value), f"{name}.{what}: ctypes {mine} != C {value}"
