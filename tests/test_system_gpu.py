@@ -183,3 +183,22 @@ def test_peer_exchange_world1_matches_plain_adam():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_peer_exchange_two_ranks_matches_nccl():
+    """N = 2 on one box: tools/peer_exchange_check.py under torchrun (gradient SUM / radii MAX / fused statistics + Adam through
+    peer memory against NCCL all-reduce + the plain kernels, replicas bit-identical). Skipped on a single-GPU box; its N = 2 and
+    N = 8 outputs are committed under profiles/r02_peer_exchange_n{2,8}.json."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "peer_exchange_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["world"] == 2 and res["P100000_p2p"]["max_rel_err_vs_nccl"] < 1e-6
