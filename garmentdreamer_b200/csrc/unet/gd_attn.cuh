@@ -304,7 +304,8 @@ k_flash_attn(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 // instead). Variants tried and dropped because they did not move the total: a quarter of the ex2 on the FMA pipe
 // (Cody-Waite polynomial; +9 instructions per score made the warps issue-bound: 2980 cycles), and sixteen softmax warps
 // with two threads per row (same 2800 cycles); ex2.approx.f16x2 on packed exponents (ptxas emits TWO scalar MUFU.EX2.F16 per
-// pair, no packed SFU op on sm_100a: 255 -> 317 us).
+// pair, no packed SFU op on sm_100a: 255 -> 317 us); an SFU token that makes the two softmax warps of a scheduler take turns
+// in the ex2 phase (one warp alone feeds the pipe at ~13 of 16 ex2/clk: 269 -> 296 us).
 constexpr int kAttn2Threads = 64 + 8 * 32;
 constexpr int kAttn2Stages = 3;
 
