@@ -181,7 +181,8 @@ def test_gemm_colstats_feed_groupnorm(ops, N, H, W, Cin, Cout):
     assert rel(out, out2) < 2e-4 and rel(stats, stats2) < 1e-4
 
 
-@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 128, 128, 128, 128), (2, 64, 64, 256, 256), (4, 64, 64, 512, 256), (1, 16, 16, 512, 512)])
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 128, 128, 128, 128), (2, 64, 64, 256, 256), (4, 64, 64, 512, 256), (1, 128, 128, 256, 256),
+                                            (1, 32, 32, 64, 512), (1, 16, 16, 512, 512)])
 def test_gemm_groupnorm_backward_producer_epilogue(ops, N, H, W, Cin, Cout):
     """Data-gradient conv whose epilogue multiplies by silu'(GN(x)) and emits sum g | sum g*xh (GdGemmArgs.gn_coef), followed by
     groupnorm_bwd on those sums, against the unfused conv + two-sweep GroupNorm backward and against torch autograd. The last
@@ -195,7 +196,8 @@ def test_gemm_groupnorm_backward_producer_epilogue(ops, N, H, W, Cin, Cout):
     d_plain = ops.groupnorm_bwd(x, plain, gam, bet, stats, silu=True, add=add)
     g = ops.conv3x3(dz_in, w, gn_bwd=(x, stats, gam, bet))
     fused_taken = bool(getattr(g, "_gd_is_g", False))
-    assert fused_taken == (N * H * W >= 4096), "fused epilogue expected for the large shapes only"
+    # (1,128,128,256->256) runs a 256-wide tile with two staging tiles per warp and few ring stages; (1,32,32,64->512) has 9 k-blocks only
+    assert fused_taken == (N * H * W >= 1024), "fused epilogue expected for every shape but the split-K one"
     d_fused = ops.groupnorm_bwd(x, g, gam, bet, stats, silu=True, add=add)
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     z = F.silu(F.group_norm(xr, 32, gam.float(), bet.float(), 1e-6))
