@@ -54,6 +54,9 @@ struct GemmKParams {
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
   float* colstats;            // optional [ceil(M/32)][2][N]: per 32-row block and output column, sum and sum of squares of the fp16
                               // values this GEMM stores (GroupNorm statistics of the consumer without another pass over the tensor)
+  int c_up2_w;                // > 0: the M rows are the pixels of a half-resolution image of this width and row m = (n, y, x) is stored at
+                              // full-resolution pixel (n, 2y, 2x) -- output row 4 (m - x) + 2 x of C (the caller offsets C by the phase
+                              // (py, px)): the per-phase GEMMs of a stride-2 data gradient write the upsampled tensor directly
   const float4* gn_coef;      // MODE 4 (GroupNorm-backward producer): [images][N] (ya, yb, ca, cb); p.residual = the GroupNorm input x.
                               // The epilogue stores g = acc * silu'(x*ya + yb) and colstats = per 32-row block sum g | sum g*(x*ca + cb)
   uint32_t halo_bytes;        // bytes of one haloed A slot (1024-aligned)
@@ -432,9 +435,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prow0 = (m_blk / p.patch_tiles_per_img) * p.rows_per_image + (t_in / p.patch_w_tiles) * 16 * p.img_w + (t_in % p.patch_w_tiles) * 8;
         pstep = p.img_w;
       }
-      auto grow = [&](int r) { return prow0 + (r >> 3) * pstep + (r & 7); };
+      auto grow = [&](int r) {
+        const int g = prow0 + (r >> 3) * pstep + (r & 7);
+        if (p.c_up2_w > 0) { const int x2 = g % p.c_up2_w; return 4 * (g - x2) + 2 * x2; }
+        return g;
+      };
+      auto rin = [&](int r) { return patch || prow0 + r < p.M; };   // row r of this tile exists (patch tiles always tile the image)
       const int row = grow(q * 32 + lane);
-      const bool row_ok = row < p.M;
+      const bool row_ok = rin(q * 32 + lane);
       const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;
       const int img = p.rows_per_image > 0 ? (m_blk * kBM + q * 32) / p.rows_per_image : 0;  // uniform per warp
       const int nlim = min(p.N, (n_blk + 1) * BN);  // columns of this tile that exist
@@ -604,7 +612,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int r = it * 8 + (lane >> 2);
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
                 const int orow = grow(q * 32 + r);
-                if (orow < p.M) {
+                if (rin(q * 32 + r)) {
                   *reinterpret_cast<uint4*>(p.C + coff + (long long)orow * p.ldc + n0 + piece * 8) = val;
                   if constexpr (gnb) {   // sum g | sum g * xh (the GroupNorm backward's two reductions)
                     const uint4 valx = *reinterpret_cast<const uint4*>(stg + 2048 + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));

@@ -831,7 +831,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     const int geglu = (a->flags & GD_EPI_GEGLU) ? 1 : 0;
     const long long mt = ((long long)a->M + gdu::kBM - 1) / gdu::kBM * a->batch;
     const bool splitk_ok = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) && a->batch == 1 && a->N % 4 == 0 &&
-                           a->c_batch_stride == 0 && a->c_head_stride == 0 && a->K / gdu::kBK >= 24;
+                           a->c_batch_stride == 0 && a->c_head_stride == 0 && a->K / gdu::kBK >= 24 && a->c_up2_w == 0;
     if (a->N <= 64) BN = (a->N + 15) / 16 * 16;
     else if (splitk_ok && mt * ((a->N + 255) / 256) <= 37) {
       // few output tiles, long K: wide tiles + split-K (below) instead of narrow tiles
@@ -866,7 +866,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   {
     const long long tiles = (long long)m_tiles_all * n_tiles_all * a->batch;
     const bool plain = !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) && a->batch == 1 && a->N % 4 == 0 &&
-                       a->c_batch_stride == 0 && a->c_head_stride == 0;
+                       a->c_batch_stride == 0 && a->c_head_stride == 0 && a->c_up2_w == 0;   // (the finalize kernel writes linear rows)
     if (plain && a->block_n <= 0 && tiles <= 74 && num_kb_all >= 24) {
       int ks = (int)(148 / tiles);
       if (ks > num_kb_all / 6) ks = num_kb_all / 6;
@@ -930,6 +930,10 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   p.row_bias_ld = a->row_bias_ld > 0 ? a->row_bias_ld : a->N;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.alpha = a->alpha; p.flags = a->flags; p.block_n = BN;
+  if (a->c_up2_w < 0 || (a->c_up2_w > 0 && (a->M % a->c_up2_w || a->batch != 1 || (a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED)) || a->colstats ||
+                                            a->residual || a->row_bias)))
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: c_up2_w needs a plain single-batch GEMM without residual / statistics and M % c_up2_w == 0");
+  p.c_up2_w = a->c_up2_w;
   const size_t b_slot_bytes = (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
   const size_t stage_bytes = a_halo ? halo_bytes + 3 * b_slot_bytes : (size_t)gdu::kBM * gdu::kBK * 2 + b_slot_bytes;
   p.a_halo = a_patch ? 2 : a_halo ? 1 : 0;
@@ -1011,7 +1015,7 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
     const int rc = make_map(&tmC, a->C, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != GD_UNET_OK) return rc;
     // 2 = staged + coalesced st.global (default); 1 = staged + TMA store (GD_GEMM_TMA_STORE=1)
-    p.tma_store = use_tma_store ? 1 : 2;
+    p.tma_store = (use_tma_store && a->c_up2_w == 0) ? 1 : 2;
   }
   // fused GroupNorm column statistics need the staged store path and whole 32-column chunks
   const bool colstats_ok = a->colstats && p.tma_store == 2 && a->N % 32 == 0 && BN % 32 == 0 && a->batch == 1 && (!a->gn_coef || gnb);

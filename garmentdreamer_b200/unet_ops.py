@@ -33,6 +33,7 @@ class GdGemmArgs(ctypes.Structure):
         ("row_bias_ld", ctypes.c_longlong),
         ("colstats", ctypes.c_void_p),
         ("gn_coef", ctypes.c_void_p),
+        ("c_up2_w", ctypes.c_int),
     ]
 
 
@@ -246,7 +247,8 @@ def _conv_box(H, W, N):
     return W, H, rows // H
 
 
-def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False, gn_bwd=None):
+def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=None, flags=0, want_stats=False, gn_bwd=None,
+              up2=None):
     """Implicit-GEMM convolution over NHWC x[N,H,W,Cx]: out[n,y,x,:] = sum_t x[n, y+dy_t, x+dx_t,
     c_t : c_t+Ck] @ w[:, t*Ck:(t+1)*Ck]^T (zero outside the image). taps = [(dx, dy, c)], w
     [Cout, len(taps)*Ck]. `out` may be a channel slice of a wider NHWC tensor."""
@@ -275,6 +277,13 @@ def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=No
     if row_bias is not None:
         a.row_bias_ld = row_bias.stride(0)
     a.alpha, a.flags = 1.0, flags
+    if up2 is not None:
+        # `out` is the FULL-resolution tensor [N,2H,2W,Cout]; this GEMM's pixel (n,y,x) lands at (n, 2y+py, 2x+px): the phase
+        # GEMMs of a stride-2 data gradient write the upsampled tensor directly
+        py, px = up2
+        assert out is not None and out.shape == (N, 2 * H, 2 * W, w.shape[0]) and out.is_contiguous()
+        a.C, a.ldc = out.data_ptr() + 2 * (py * 2 * W + px) * w.shape[0], w.shape[0]
+        a.c_up2_w = W
     if gn_bwd is not None and _FUSE_GN_BWD:
         # this GEMM is the data gradient in front of a GroupNorm+SiLU backward: gn_bwd = (x, stats, gamma, beta) of that GroupNorm
         gx, gstats, ggamma, gbeta = gn_bwd

@@ -31,6 +31,7 @@ GRAD_TARGET = 16.0   # the fp16 backward chain starts with max |d moments| in [8
 _DOWN_TAPS = [((kx >> 1), (ky >> 1), ((ky & 1) * 2 + (kx & 1))) for ky in range(3) for kx in range(3)]
 
 
+_DGRAD_DIRECT = __import__("os").environ.get("GD_VAE_DGRAD_DIRECT", "1") != "0"
 _GN_BWD_FUSE_MIN_C = int(__import__("os").environ.get("GD_GN_BWD_FUSE_MIN_C", "256"))
 
 
@@ -149,11 +150,19 @@ class VAEEncoderB200:
     def _down_bwd(self, rec, dout):
         _, p, C = rec
         N, Ho, Wo, Cout = dout.shape
-        ds2d = torch.empty((N, Ho, Wo, 4 * C), dtype=torch.float16, device=dout.device)
-        for ph in range(4):
-            taps = [(-(kx >> 1), -(ky >> 1), 0) for ky in range(3) for kx in range(3) if (ky & 1) * 2 + (kx & 1) == ph]
-            ops.conv_taps(dout, self.w[f"{p}.bwd{ph}"], taps, Cout, out=ds2d[..., ph * C:(ph + 1) * C])
-        din = ops.depth_to_space(ds2d)
+        if _DGRAD_DIRECT:
+            # the GEMM of phase (py, px) stores its pixel (y, x) at (2y + py, 2x + px) of the full-resolution gradient itself
+            # (GdGemmArgs.c_up2_w): no [N,Ho,Wo,4C] intermediate and no depth-to-space pass
+            din = torch.empty((N, 2 * Ho, 2 * Wo, C), dtype=torch.float16, device=dout.device)
+            for ph in range(4):
+                taps = [(-(kx >> 1), -(ky >> 1), 0) for ky in range(3) for kx in range(3) if (ky & 1) * 2 + (kx & 1) == ph]
+                ops.conv_taps(dout, self.w[f"{p}.bwd{ph}"], taps, Cout, out=din, up2=(ph >> 1, ph & 1))
+        else:
+            ds2d = torch.empty((N, Ho, Wo, 4 * C), dtype=torch.float16, device=dout.device)
+            for ph in range(4):
+                taps = [(-(kx >> 1), -(ky >> 1), 0) for ky in range(3) for kx in range(3) if (ky & 1) * 2 + (kx & 1) == ph]
+                ops.conv_taps(dout, self.w[f"{p}.bwd{ph}"], taps, Cout, out=ds2d[..., ph * C:(ph + 1) * C])
+            din = ops.depth_to_space(ds2d)
         if self._trace is not None:
             self._trace("down_bwd", p, (None, dout), din)
         return din

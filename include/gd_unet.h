@@ -85,6 +85,10 @@ typedef struct {
      gd_unet_groupnorm_bwd_g turns into dx without a statistics sweep over x and dz. Returns GD_UNET_NO_COLSTATS when the
      shape cannot take this epilogue: C then holds the PLAIN product (residual ignored), use gd_unet_groupnorm_bwd. */
   const void* gn_coef;
+  /* > 0: the M rows are the pixels (n, y, x) of a half-resolution image of this width and row m is stored at the full-resolution
+     pixel (n, 2y, 2x): output row 4*(m - x) + 2*x of C (the caller offsets C by the phase (py, px): + (py*2*w + px) rows). The
+     four per-phase GEMMs of a stride-2 convolution's data gradient write the upsampled tensor directly (no depth-to-space). */
+  int c_up2_w;
 } GdGemmArgs;
 
 int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
