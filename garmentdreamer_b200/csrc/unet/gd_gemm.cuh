@@ -54,6 +54,8 @@ struct GemmKParams {
   float* ws;                  // [ksplit][M][N] partial sums (deterministic: summed in order by k_splitk_finalize)
   float* colstats;            // optional [ceil(M/32)][2][N]: per 32-row block and output column, sum and sum of squares of the fp16
                               // values this GEMM stores (GroupNorm statistics of the consumer without another pass over the tensor)
+  int a_yscale;               // conv taps: A row coordinate = tile row * a_yscale + tap_dy (2: stride-2 convolution read through a strided
+                              // VIEW of the full-resolution input, dims {2C, W/2, H, N}: no space-to-depth copy)
   int c_up2_w;                // > 0: the M rows are the pixels of a half-resolution image of this width and row m = (n, y, x) is stored at
                               // full-resolution pixel (n, 2y, 2x) -- output row 4 (m - x) + 2 x of C (the caller offsets C by the phase
                               // (py, px)): the per-phase GEMMs of a stride-2 data gradient write the upsampled tensor directly
@@ -320,7 +322,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (rank == 0) bar_expect_tx(&full[s], bres ? 2 * a_bytes : 2 * (a_bytes + b_bytes));
             if (p.mode_conv) {
               const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
-              tma_load_4d_2sm(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+              tma_load_4d_2sm(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 * p.a_yscale + p.tap_dy[tap], a_c3);
             } else {
               tma_load_4d_2sm(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
             }
@@ -329,7 +331,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bar_expect_tx(&full[s], a_bytes + b_bytes);
             if (p.mode_conv) {
               const int tap = kb / p.kb_per_tap, cb = kb % p.kb_per_tap;
-              tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 + p.tap_dy[tap], a_c3);
+              tma_load_4d(sa, &tmA, &full[s], p.tap_c[tap] + cb * kBK, a_c1 + p.tap_dx[tap], a_c2 * p.a_yscale + p.tap_dy[tap], a_c3);
             } else {
               tma_load_4d(sa, &tmA, &full[s], zh * p.a_head_k + kb * kBK, a_c1, a_c2, a_c3);
             }

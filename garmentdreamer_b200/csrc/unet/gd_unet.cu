@@ -880,13 +880,13 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
   // haloed A tiles (one 130-pixel row per (dy, channel block) instead of three 128-pixel rows): 3x3 stride-1 convolutions over
   // images at least 128 pixels wide, CTA pairs, plain epilogue. GD_GEMM_HALO=0 switches it off (A/B timing).
   static const bool halo_enabled = []() { const char* e = getenv("GD_GEMM_HALO"); return !(e && e[0] == '0'); }();
-  bool a_halo = halo_enabled && two && a->ntaps == 9 && a->a_box[1] == gdu::kBM && a->a_box[2] == 1 && a->a_box[3] == 1 && a->Ck % gdu::kBK == 0;
+  bool a_halo = halo_enabled && a->a_yscale != 2 && two && a->ntaps == 9 && a->a_box[1] == gdu::kBM && a->a_box[2] == 1 && a->a_box[3] == 1 && a->Ck % gdu::kBK == 0;
   for (int t = 0; a_halo && t < 9; t++) a_halo = a->tap_dx[t] == t % 3 - 1 && a->tap_dy[t] == t / 3 - 1 && a->tap_c[t] == 0;
   // images narrower than 128 pixels: M tiles become 8 x 16 pixel patches with a haloed A slot per (dy, channel block), see
   // GemmKParams.a_halo == 2. GD_GEMM_PATCH=0 switches it off (A/B timing).
   static const bool patch_enabled = []() { const char* e = getenv("GD_GEMM_PATCH"); return !(e && e[0] == '0'); }();
   static const bool tma_store_env = []() { const char* e = getenv("GD_GEMM_TMA_STORE"); return e && e[0] == '1'; }();
-  bool a_patch = patch_enabled && !tma_store_env && !a_halo && two && a->ntaps == 9 && a->a_box[1] < gdu::kBM && a->a_box[3] == 1 &&
+  bool a_patch = patch_enabled && a->a_yscale != 2 && !tma_store_env && !a_halo && two && a->ntaps == 9 && a->a_box[1] < gdu::kBM && a->a_box[3] == 1 &&
                  a->img_w % 8 == 0 && a->img_h % 16 == 0 && a->Ck % gdu::kBK == 0 && !(a->flags & (GD_EPI_GEGLU | GD_EPI_TRANSPOSED));
   for (int t = 0; a_patch && t < 9; t++) a_patch = a->tap_dx[t] == t % 3 - 1 && a->tap_dy[t] == t / 3 - 1 && a->tap_c[t] == 0;
   const size_t halo_bytes = a_patch ? (size_t)gdu::kPatchBytes : (size_t)gdu::kHaloBytes;
@@ -934,6 +934,9 @@ int gd_unet_gemm(const GdGemmArgs* a, gd_ustream_t stream_) {
                                             a->residual || a->row_bias)))
     return fail(GD_UNET_ERR_INVALID_ARG, "gemm: c_up2_w needs a plain single-batch GEMM without residual / statistics and M % c_up2_w == 0");
   p.c_up2_w = a->c_up2_w;
+  if (a->a_yscale < 0 || a->a_yscale > 2 || (a->a_yscale == 2 && (a->ntaps < 1 || a->a_box[2] != 1 || a->a_box[3] != 1)))
+    return fail(GD_UNET_ERR_INVALID_ARG, "gemm: a_yscale = 2 needs a tap GEMM whose A box is part of one image row");
+  p.a_yscale = a->a_yscale == 2 ? 2 : 1;
   const size_t b_slot_bytes = (((size_t)(two ? BN / 2 : BN) * gdu::kBK * 2 + 1023) & ~(size_t)1023);
   const size_t stage_bytes = a_halo ? halo_bytes + 3 * b_slot_bytes : (size_t)gdu::kBM * gdu::kBK * 2 + b_slot_bytes;
   p.a_halo = a_patch ? 2 : a_halo ? 1 : 0;

@@ -34,6 +34,7 @@ class GdGemmArgs(ctypes.Structure):
         ("colstats", ctypes.c_void_p),
         ("gn_coef", ctypes.c_void_p),
         ("c_up2_w", ctypes.c_int),
+        ("a_yscale", ctypes.c_int),
     ]
 
 
@@ -302,6 +303,36 @@ def conv_taps(x, w, taps, Ck, bias=None, *, row_bias=None, residual=None, out=No
             out._gd_colstats = (stats, a.N) if rc == 0 else None
             out._gd_is_g = rc == 0
             return out
+    _gemm(a, out, want_stats)
+    return out
+
+
+def conv_stride2_view(x, w, offsets, bias=None, *, out=None, want_stats=False):
+    """Stride-2 convolution over NHWC x[N,H,W,C] WITHOUT a space-to-depth copy (needs W/2 >= 128): output pixel (y, x) sums
+    taps t over input pixels (2y + oy_t, 2x + ox_t), offsets = [(ox, oy)] in the order of w[Cout, len(offsets)*C]; zero
+    outside the image. A is read through a strided view {2C, W/2, H, N} of x (GdGemmArgs.a_yscale = 2)."""
+    _h(x); _h(w)
+    N, H, W, C = x.shape
+    Ho, Wo, Cout, nt = H // 2, W // 2, w.shape[0], len(offsets)
+    assert Wo % 128 == 0 and H % 2 == 0 and C % 64 == 0
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float16, device=x.device)
+    a = GdGemmArgs()
+    a.M, a.N, a.K, a.batch, a.heads = N * Ho * Wo, Cout, nt * C, 1, 1
+    a.A = x.data_ptr()
+    a.a_dim[:] = [2 * C, Wo, H, N]
+    a.a_stride[:] = [2 * C * 2, W * C * 2, H * W * C * 2]
+    a.a_box[:] = [64, 128, 1, 1]
+    a.ntaps, a.Ck = nt, C
+    for t, (ox, oy) in enumerate(offsets):
+        a.tap_dx[t], a.tap_dy[t], a.tap_c[t] = ox >> 1, oy, (ox & 1) * C
+    a.rows_per_image, a.img_w, a.img_h = Ho * Wo, Wo, Ho
+    a.B = w.data_ptr()
+    a.b_dim[:] = [nt * C, Cout, 1]
+    a.b_stride[:] = [nt * C * 2, Cout * nt * C * 2]
+    a.C, a.ldc = out.data_ptr(), Cout
+    a.bias = _p(bias)
+    a.alpha, a.a_yscale = 1.0, 2
     _gemm(a, out, want_stats)
     return out
 

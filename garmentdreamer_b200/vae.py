@@ -31,6 +31,7 @@ GRAD_TARGET = 16.0   # the fp16 backward chain starts with max |d moments| in [8
 _DOWN_TAPS = [((kx >> 1), (ky >> 1), ((ky & 1) * 2 + (kx & 1))) for ky in range(3) for kx in range(3)]
 
 
+_DOWN_VIEW = __import__("os").environ.get("GD_VAE_DOWN_VIEW", "1") != "0"
 _DGRAD_DIRECT = __import__("os").environ.get("GD_VAE_DGRAD_DIRECT", "1") != "0"
 _GN_BWD_FUSE_MIN_C = int(__import__("os").environ.get("GD_GN_BWD_FUSE_MIN_C", "256"))
 
@@ -138,11 +139,16 @@ class VAEEncoderB200:
         return din
 
     def _down_fwd(self, p, x, saved):
-        s2d = ops.space_to_depth(x)
         C = x.shape[-1]
-        taps = [(dx, dy, ph * C) for dx, dy, ph in _DOWN_TAPS]
         saved.append(("down", p, C))
-        out = ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"], want_stats=True)
+        if _DOWN_VIEW and (x.shape[2] // 2) % 128 == 0:
+            # pad (0,1,0,1), stride 2: output (y, x) reads input (2y + ky, 2x + kx) through a strided view of x -- no space-to-depth copy
+            out = ops.conv_stride2_view(x, self.w[p + ".fwd"], [(kx, ky) for ky in range(3) for kx in range(3)], self.w[p + ".bias"],
+                                        want_stats=True)
+        else:
+            s2d = ops.space_to_depth(x)
+            taps = [(dx, dy, ph * C) for dx, dy, ph in _DOWN_TAPS]
+            out = ops.conv_taps(s2d, self.w[p + ".fwd"], taps, C, self.w[p + ".bias"], want_stats=True)
         if self._trace is not None:
             self._trace("down", p, x, out)
         return out

@@ -89,6 +89,10 @@ typedef struct {
      pixel (n, 2y, 2x): output row 4*(m - x) + 2*x of C (the caller offsets C by the phase (py, px): + (py*2*w + px) rows). The
      four per-phase GEMMs of a stride-2 convolution's data gradient write the upsampled tensor directly (no depth-to-space). */
   int c_up2_w;
+  /* 2: stride-2 convolution without a space-to-depth copy. A is a strided VIEW of the full-resolution NHWC input with dims
+     {2C, W/2, H, N} (a pixel pair is one 2C-channel super-pixel); output row y reads input row 2*y + tap_dy, tap_dx shifts
+     super-pixels and tap_c selects the pixel of the pair (0 or C). Needs an A box inside one image row (W/2 >= 128). 0/1: off. */
+  int a_yscale;
 } GdGemmArgs;
 
 int gd_unet_gemm(const GdGemmArgs* args, gd_ustream_t stream);
