@@ -442,7 +442,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.c_up2_w > 0) { const int x2 = g % p.c_up2_w; return 4 * (g - x2) + 2 * x2; }
         return g;
       };
-      auto rin = [&](int r) { return patch || prow0 + r < p.M; };   // row r of this tile exists (patch tiles always tile the image)
+      auto rin = [&](int r) { return m_blk * kBM + r < p.M; };   // row r of this tile exists (also false for the phantom second tile
+                                                                 // of a pair when the tile count is odd)
       const int row = grow(q * 32 + lane);
       const bool row_ok = rin(q * 32 + lane);
       const long long coff = (long long)zb * p.c_batch_stride + (long long)zh * p.c_head_stride;

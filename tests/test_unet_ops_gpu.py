@@ -71,6 +71,19 @@ def test_conv3x3(ops, N, H, W, Cin, Cout):
     assert maxrel(y, ref) < 2e-3 and rel(y, ref) < 1e-3
 
 
+def test_conv3x3_patch_tiles_odd_tile_count_stays_in_bounds(ops):
+    """Patch tiles (8 px x 16 rows) with an ODD number of tiles: the second CTA of the last pair owns a tile that does not exist
+    and must neither store nor count statistics for it (guard words behind the output stay untouched)."""
+    N, H, W, Cin, Cout = 3, 16, 8, 128, 64
+    x, w, b = rnd(N, H, W, Cin), rnd(Cout, 3, 3, Cin, scale=(9 * Cin) ** -0.5), rnd(Cout)
+    buf = torch.full((N * H * W * Cout + 4096,), 7.0, dtype=torch.float16, device="cuda")
+    out = buf[:N * H * W * Cout].view(N, H, W, Cout)
+    y = ops.conv3x3(x, w, b, out=out, want_stats=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel(y, ref) < 1e-3
+    assert bool((buf[N * H * W * Cout:] == 7.0).all()), "stores behind the end of the output tensor"
+
+
 @pytest.mark.parametrize("N,H,W,C", [(2, 64, 64, 320), (2, 32, 32, 640), (2, 16, 16, 1280)])
 def test_conv3x3_stride2(ops, N, H, W, C):
     x, w, b = rnd(N, H, W, C), rnd(C, 3, 3, C, scale=(9 * C) ** -0.5), rnd(C)
